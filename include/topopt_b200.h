@@ -1,0 +1,163 @@
+/*
+ * topopt_b200.h — C ABI of libtopopt_b200.so
+ *
+ * B200-native (sm_100a) replacement of the strain-energy evaluation path of jezekon/TopOptEval.jl:
+ * element stiffness → sparse assembly → loads / Dirichlet → Jacobi-PCG → per-element energy / compliance.
+ *
+ * The reference has no FFI of its own: its boundary is the Julia function API of
+ * TopOptEval.FiniteElementAnalysis (export list src/FiniteElementAnalysis/FiniteElementAnalysis.jl:11-24,
+ * 75-87).  Each entry point below names the reference function whose body it replaces; the Julia `ccall`
+ * shim (topopteval.jl_b200/julia/TopOptEvalB200.jl) and the Python ctypes mirror
+ * (topopteval.jl_b200/api.py) keep the reference's names and argument order on top of these calls.
+ *
+ * Conventions
+ *   - every function returns int status: 0 = OK, <0 = error (toe_last_error() gives the text; the Julia shim
+ *     turns it into `error(msg)` like the reference's own `error(...)` calls, e.g. FiniteElementAnalysis.jl:394);
+ *   - all indices that cross the ABI are int64 and **1-based** (Julia's Int), all reals are double;
+ *   - host pointers are caller-owned, read/written only during the call; device state is owned by the ctx;
+ *   - a ctx is driven by one host thread at a time; distinct contexts are independent (one ctx per GPU);
+ *   - there is NO CPU fallback: without a usable sm_100 device toe_create fails.
+ */
+#ifndef TOPOPT_B200_H
+#define TOPOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct toe_ctx toe_ctx;
+
+/* assembly variants (toe_assemble_*) */
+#define TOE_ASM_AUTO    0   /* = TOE_ASM_GATHER */
+#define TOE_ASM_ATOMIC  1   /* one thread per element, red.global.add.f64 scatter */
+#define TOE_ASM_GATHER  2   /* one thread per 3x3 block of K, loops its contributing elements in ascending
+                               cell order (the reference's accumulation order, Ferrite assemble!): no atomics,
+                               deterministic, coalesced writes */
+
+/* toe_solve_pcg flags */
+#define TOE_PCG_MATRIX_FREE   1   /* element-by-element operator, K is not read (nor needed) */
+#define TOE_PCG_NO_GRAPH      2   /* launch kernels directly instead of replaying a CUDA graph */
+
+typedef struct toe_pcg_stats {
+    int64_t niter;            /* Krylov.jl stats.niter */
+    int32_t converged;        /* Krylov.jl stats.solved: sqrt(r'Mr) <= atol + rtol*sqrt(r0'Mr0) */
+    int32_t breakdown;        /* 1 if p'Ap <= 0 was met (Krylov.jl stops there) */
+    double  res0_M;           /* sqrt(r0' M r0) */
+    double  res_M;            /* final sqrt(r' M r) */
+    double  rel_res_l2;       /* ||f - K u||_2 / ||f||_2, recomputed after the solve (RobustSolver.jl:468) */
+    double  solve_seconds;    /* device time of the iteration loop (CUDA events) */
+    double  spmv_seconds;     /* niter x average operator time, measured on a few isolated launches after the solve */
+    double  spmv_bytes;       /* algorithmic bytes of one operator application */
+    int64_t kernel_launches;  /* kernels launched by this call */
+} toe_pcg_stats;
+
+typedef struct toe_timings {  /* device seconds of the last call of each stage (CUDA events) */
+    double set_mesh, build_dofs, build_pattern, assemble, loads, dirichlet, solve, energy;
+    int64_t kernel_launches;  /* total kernels launched by this ctx so far */
+} toe_timings;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+int         toe_version(void);
+int         toe_create(int device, toe_ctx** out);
+void        toe_destroy(toe_ctx* ctx);
+const char* toe_last_error(toe_ctx* ctx);            /* ctx may be NULL: error of the last failed toe_create */
+int         toe_get_timings(toe_ctx* ctx, toe_timings* out);
+
+/* ---- setup_problem (FiniteElementAnalysis.jl:151-185) ------------------------------------------------ */
+/* xyz: 3*nn doubles, node-major (= Julia 3×nn column-major, grid.nodes); conn: npc*ne int64, 1-based,
+ * cell-major (= Julia npc×ne column-major, grid.cells); npc = 4 (Tetrahedron) or 8 (Hexahedron), chosen by
+ * the caller from typeof(getcells(grid,1)) as :157 does.  Rejects npc∉{4,8} and out-of-range node ids. */
+int toe_set_mesh(toe_ctx* ctx, int64_t nn, const double* xyz, int64_t ne, int npc, const int64_t* conn);
+/* Ferrite close!(dh) (:174-176): first-touch numbering, 3 consecutive DOFs per node. */
+int toe_build_dofs(toe_ctx* ctx, int64_t* ndofs_out);
+/* node_first_dof[nn]: first DOF of each node (1-based), 0 for nodes in no cell  (what get_node_dofs :265-293 rebuilds) */
+int toe_get_node_dofs(toe_ctx* ctx, int64_t* node_first_dof);
+/* celldofs of cells first..first+count-1 (1-based), 3*npc each — dh.cell_dofs */
+int toe_get_cell_dofs(toe_ctx* ctx, int64_t first, int64_t count, int64_t* out);
+/* Ferrite allocate_matrix(dh) (:181): sparsity of K.  Pattern is structurally symmetric, so colptr/rowval
+ * (CSC, 1-based, rows ascending per column) double as CSR rowptr/colind. */
+int toe_build_pattern(toe_ctx* ctx, int64_t* nnz_out);
+int toe_get_pattern(toe_ctx* ctx, int64_t* colptr /* ndofs+1 */, int64_t* rowval /* nnz */);
+
+/* ---- assembly (FiniteElementAnalysis.jl:204-250, 654-707) -------------------------------------------- */
+/* All three zero K and f first (start_assemble, :211/:661), reject det J <= 0 (Ferrite reinit!). */
+/* assemble_stiffness_matrix!(K,f,dh,cv,λ,μ) */
+int toe_assemble_lame(toe_ctx* ctx, double lambda, double mu, int variant);
+/* assemble_stiffness_matrix_simp! with the closure of create_simp_material_model(E0,nu,Emin,p) (:616-634):
+ * E = Emin + (E0-Emin)*density^p evaluated in the kernel. density: ne doubles. */
+int toe_assemble_simp(toe_ctx* ctx, double E0, double nu, double Emin, double p, const double* density, int variant);
+/* assemble_stiffness_matrix_simp! with an arbitrary material_model: the shim evaluates it on the host. */
+int toe_assemble_lame_per_cell(toe_ctx* ctx, const double* lambda_e, const double* mu_e, int variant);
+/* Sets the material exactly like the calls above but does not form K (matrix-free solves). Zeroes f. */
+int toe_set_material_lame(toe_ctx* ctx, double lambda, double mu);
+int toe_set_material_simp(toe_ctx* ctx, double E0, double nu, double Emin, double p, const double* density);
+/* parity hook: Ke of cells first..first+count-1 (1-based), (3npc)^2 doubles each, column-major, with the
+ * material of the last assemble/set_material call. */
+int toe_ke_batch(toe_ctx* ctx, int64_t first, int64_t count, double* ke_out);
+/* K.nzval in the order of toe_get_pattern */
+int toe_get_values(toe_ctx* ctx, double* nzval);
+int toe_get_diagonal(toe_ctx* ctx, double* diag /* ndofs */);
+
+/* ---- loads ----------------------------------------------------------------------------------------- */
+int toe_get_rhs(toe_ctx* ctx, double* f);
+int toe_set_rhs(toe_ctx* ctx, const double* f);      /* lets host-side loads (surface-traction callbacks) flow in */
+/* apply_force!(f,dh,nodes,F) (:392-418): f[dofs(node)] += F/nnodes; nnodes==0 is an error (:393-395);
+ * nodes that belong to no cell are skipped (haskey, :402). */
+int toe_add_nodal_force(toe_ctx* ctx, const int64_t* nodes, int64_t nnodes, const double F[3]);
+/* apply_volume_force!/apply_gravity!/apply_acceleration! (VolumeForce.jl:26-159): density==NULL, load per
+ * cell = rho_uniform*(b/rho_uniform)*N*dΩ.  apply_variable_density_volume_force! (:176-243): density!=NULL,
+ * cells with density < skip_below (reference: 1e-6, :199) are skipped.  total_force_out[3] may be NULL. */
+int toe_add_volume_force(toe_ctx* ctx, const double b[3], double rho_uniform, const double* density,
+                         double skip_below, double* total_force_out);
+
+/* ---- Dirichlet: Ferrite apply!(K,f,ch) (call sites :540-542, :841-843, RobustSolver.jl:542-544) ------- */
+/* zero-valued constraints on dofs (1-based): m = mean(abs(diag K)) of the incoming K, stored entries of the
+ * prescribed rows and columns become 0.0, K[d,d] = m, f[d] = 0.  Call once per ConstraintHandler, in order. */
+int toe_apply_dirichlet(toe_ctx* ctx, const int64_t* dofs, int64_t ndofs, double* mean_diag_out);
+
+/* ---- solve: solve_with_krylov(:cg, :diagonal) (RobustSolver.jl:223-236, 279-338) ---------------------- */
+/* Krylov.jl cg semantics: x0 = 0, M = Diagonal(1 ./ D) with D[abs(D)<1e-12] = 1, stop on the M-norm test.
+ * history (may be NULL): sqrt(r'Mr) per iteration, history_cap entries at most (stats.residuals). */
+int toe_solve_pcg(toe_ctx* ctx, double atol, double rtol, int64_t itmax, int flags,
+                  toe_pcg_stats* stats, double* history, int64_t history_cap);
+int toe_get_solution(toe_ctx* ctx, double* u /* ndofs, Ferrite dof order */);
+int toe_set_solution(toe_ctx* ctx, const double* u);  /* evaluate energies of a displacement field computed elsewhere */
+
+/* ---- energy (FiniteElementAnalysis.jl:550, :851; RobustSolver.jl:604, :717) --------------------------- */
+/* half_uKu = 0.5*dot(u,K*u) (sum of the per-element energies ½ uₑᵀKₑuₑ), compliance = f'u,
+ * per_elem (ne doubles, may be NULL). */
+int toe_energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem);
+/* the reference's exact expression with the assembled, constrained K (one SpMV + dot) */
+int toe_energy_assembled(toe_ctx* ctx, double* half_uKu);
+
+/* ---- stress recovery: calculate_stresses(_simp) (:440-509, :730-801) ---------------------------------- */
+/* sigma (may be NULL): 6 x nqp x ne doubles (xx,yy,zz,xy,yz,xz per quadrature point, nqp = 4 tet / 8 hex);
+ * von_mises (may be NULL): ne doubles, von Mises of the qp-averaged stress; max + 1-based argmax (first max wins). */
+int toe_stresses(toe_ctx* ctx, double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell);
+
+/* ---- operator hooks for tests and bench ----------------------------------------------------------- */
+/* y = K x with the current (possibly constrained) operator; matrix_free selects the EbE kernel. */
+int toe_spmv(toe_ctx* ctx, const double* x, double* y, int matrix_free);
+/* times `reps` back-to-back operator applications on device vectors; returns average seconds and the
+ * algorithmic bytes of one application. */
+int toe_time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out);
+
+/* ---- multi-GPU: one ctx per GPU / process, element-based domain decomposition --------------------------- */
+/* NCCL (dlopen'ed libnccl.so.2) send/recv for the interface-DOF exchange and allreduce for the CG scalars.
+ * Rank 0 creates the id, the host (torch.distributed / MPI / Distributed.jl) broadcasts its 128 bytes. */
+int toe_comm_unique_id(char id_out[128]);
+int toe_comm_init(toe_ctx* ctx, int nranks, int rank, const char id[128]);
+/* Must be called after toe_comm_init and instead of toe_set_mesh: every rank passes the SAME global mesh;
+ * the library numbers DOFs globally (identical to the 1-GPU numbering), splits the cells by recursive
+ * coordinate bisection of their centroids and keeps only this rank's part (+ interface maps). */
+int toe_set_mesh_distributed(toe_ctx* ctx, int64_t nn, const double* xyz, int64_t ne, int npc, const int64_t* conn);
+/* part id (0-based) of every global cell (ne int32) — identical on all ranks */
+int toe_get_partition(toe_ctx* ctx, int32_t* part_of_cell);
+int toe_local_sizes(toe_ctx* ctx, int64_t* ne_local, int64_t* ndofs_local, int64_t* nnz_local, int64_t* n_interface_dofs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPOPT_B200_H */

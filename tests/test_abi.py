@@ -1,0 +1,51 @@
+"""CPU checks of the drop-in boundary: the shared library builds for sm_100a, loads, and exports every symbol that
+include/topopt_b200.h declares; without a GPU the product path fails loudly instead of falling back."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "topopt_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(toe_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_are_exported_and_bound(pkg):
+    import __graft_entry__ as graft
+    graft.build()
+    lib = pkg._lib.load()
+    names = _declared()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), "libtopopt_b200.so does not export %s" % n
+        assert n in pkg._lib.SIGNATURES, "ctypes binding lacks %s" % n
+    assert sorted(pkg._lib.SIGNATURES) == names
+    assert lib.toe_version() == 100
+
+
+def test_library_is_sm100a_only():
+    so = os.path.join(ROOT, "topopteval.jl_b200", "libtopopt_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback(pkg, have_gpu):
+    if have_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.TopOptError, match="no CPU fallback|no CUDA device"):
+        pkg.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    pdir = os.path.join(ROOT, "topopteval.jl_b200")
+    for dp, _, files in os.walk(pdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".jl")):
+                src = open(os.path.join(dp, f)).read()
+                assert "fea_oracle" not in src and "oracle/" not in src and "import oracle" not in src, f

@@ -1,0 +1,98 @@
+"""CPU tests of the oracle itself: frozen golden values (tests/golden, generated from the reference's fixtures by
+tests/golden/make_golden.py), internal consistency of the restatement, and the reference's one analytic check."""
+import hashlib
+
+import numpy as np
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_golden_c1_setup_and_assembly(fo, golden_c1):
+    g = golden_c1
+    pts, cells = g["points"], g["cells"].astype(np.int64)
+    prob = fo.setup_problem(pts, cells)
+    assert prob.ndofs == int(g["ndofs"]) == 8631 and prob.nnz == int(g["nnz"]) == 275751
+    assert np.array_equal(prob.node_first_dof, g["node_first_dof"])
+    assert sha(prob.colptr) == str(g["colptr_sha"]) and sha(prob.rowval) == str(g["rowval_sha"])
+    assert np.max(np.diff(prob.colptr)) == 102                      # max 102 entries per row
+    lam, mu = fo.create_material_model(1.0, 0.3)
+    ke = fo.assemble_stiffness_matrix(prob, lam, mu)
+    assert np.allclose(ke[g["ke_sample_ids"] - 1], g["ke_sample"], rtol=0, atol=1e-13 * np.abs(g["ke_sample"]).max())
+    fo.apply_force(prob, g["load_nodes"], [0.0, 0.0, -1.0])
+    assert np.array_equal(prob.f, g["f_loaded"])
+    pres = fo.fixed_boundary_dofs(prob, g["fixed_nodes"])
+    assert np.array_equal(pres, g["prescribed"]) and pres.size == 120
+    m = fo.apply_dirichlet(prob, pres)
+    assert abs(m - 8.2395090017) < 1e-9 and abs(m - float(g["mean_diag"])) < 1e-13
+    u = fo.solve_direct(prob)
+    assert np.linalg.norm(u - g["u"]) <= 1e-9 * np.linalg.norm(g["u"])
+    e = fo.deformation_energy(prob, u)
+    assert abs(e - 621.854208) < 1e-5 and abs(e - float(g["energy"])) <= 1e-9 * e
+    ee = fo.element_energies(prob, u, ke)
+    assert abs(ee.sum() / e - 1) < 1e-9
+
+
+def test_golden_c2_values(fo, golden_c2):
+    g = golden_c2
+    assert int(g["ndofs"]) == 19215 and int(g["nnz"]) == 1291797
+    assert abs(float(g["mean_diag"]) - 0.54980907499) < 1e-10
+    assert abs(float(g["energy"]) / 4.1716953103e7 - 1) < 1e-9
+    assert abs(float(g["vf_energy"]) / 3.7668677048e8 - 1) < 1e-9
+    assert abs(g["vf_f_loaded"].sum() + 1923.3236661882) < 1e-6
+    rho = g["density"]
+    assert rho.size == 4800 and (rho < 1e-6).sum() == 2708
+
+
+def test_first_touch_literal_equals_vectorised(fo, pkg):
+    pts, cells = pkg.meshgen.cantilever(5, 3, 2)
+    cells = cells[np.random.default_rng(0).permutation(cells.shape[0])]
+    a = fo.first_touch_dofs(cells, pts.shape[0]); b = fo.first_touch_dofs_literal(cells, pts.shape[0])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    assert not np.array_equal(a[0], 3 * np.arange(pts.shape[0]) + 1)       # F8: not the identity map
+
+
+def test_ke_literal_loop_equals_batched(fo, golden_c1, golden_c2):
+    for g in (golden_c1, golden_c2):
+        pts, cells = g["points"], g["cells"].astype(np.int64)
+        e = 17
+        lit = fo.element_stiffness_literal(pts[cells[e] - 1], 0.7, 0.4)
+        bat = fo.element_stiffness(pts, cells[e:e + 1], 0.7, 0.4)[0]
+        assert np.max(np.abs(lit - bat)) <= 1e-13 * np.abs(lit).max()
+        # closed form quoted in SURVEY §3.2
+        assert np.max(np.abs(lit - lit.T)) <= 1e-12 * np.abs(lit).max()
+        assert np.max(np.abs(lit @ np.tile(np.eye(3), (cells.shape[1], 1)))) <= 1e-12 * np.abs(lit).max()   # rigid translations
+
+
+def test_pcg_matches_direct(fo, golden_syn, pkg):
+    pts, cells = pkg.meshgen.cantilever(12, 4, 2)
+    prob = fo.setup_problem(pts, cells)
+    lam, mu = fo.create_material_model(1.0, 0.3)
+    fo.assemble_stiffness_matrix(prob, lam, mu)
+    fo.apply_force(prob, pkg.meshgen.nodes_at_plane(pts, 0, 60.0), [0, 0, -1.0])
+    fo.apply_dirichlet(prob, fo.fixed_boundary_dofs(prob, pkg.meshgen.nodes_at_plane(pts, 0, 0.0)))
+    u = fo.solve_direct(prob)
+    x, st = fo.solve_pcg(prob, 1e-8, 10000)
+    assert st["solved"] and st["niter"] == int(golden_syn["12x4x2_pcg_niter"]) == 377
+    assert np.linalg.norm(x - u) <= 1e-9 * np.linalg.norm(u)
+    assert abs(fo.deformation_energy(prob, u) - 98.86975939) < 1e-6
+    assert len(st["residuals"]) == st["niter"] + 1
+
+
+def test_gravity_cantilever_known_answer(fo, pkg):
+    """test/VolumeForces/testVolumeForces.jl:8-37,159-168 — the reference's only analytic check (<10 %)."""
+    L, h = 10.0, 1.0
+    pts, cells = pkg.meshgen.cantilever(40, 8, 8, L=(L, h, h), hex=True)
+    E, nu, rho, g = 200e9, 0.3, 7850.0, 9.81
+    prob = fo.setup_problem(pts, cells)
+    fo.assemble_stiffness_matrix(prob, *fo.create_material_model(E, nu))
+    tot, vol = fo.apply_gravity(prob, rho, g, [0.0, 0.0, -1.0])
+    assert abs(vol - L * h * h) < 1e-9 and abs(tot[2] + rho * g * vol) < 1e-6 * rho * g
+    fo.apply_dirichlet(prob, fo.fixed_boundary_dofs(prob, pkg.meshgen.nodes_at_plane(pts, 0, 0.0)))
+    u = fo.solve_direct(prob)
+    tip = pkg.meshgen.nodes_at_plane(pts, 0, L)
+    defl = np.abs(u[prob.node_first_dof[tip - 1] + 1]).max()
+    analytic = rho * g * L ** 4 / (8 * E * (h ** 4 / 12))
+    assert abs(analytic - 5.7756375e-3) < 1e-9
+    assert abs(defl - analytic) / analytic < 0.10

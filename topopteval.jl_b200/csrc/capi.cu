@@ -1,0 +1,271 @@
+// capi.cu — extern "C" entry points of libtopopt_b200.so (see include/topopt_b200.h for the contract and for the
+// reference function each call replaces).
+#include "common.cuh"
+#include <cstring>
+#include <mutex>
+
+// implemented in the other translation units
+int assemble_current_material(toe_ctx* ctx, int variant);
+int ke_batch(toe_ctx* ctx, i64 first, i64 count, double* out_host);
+int add_nodal_force(toe_ctx* ctx, const int64_t* nodes, i64 nnodes, const double F[3]);
+int add_volume_force(toe_ctx* ctx, const double b[3], double rho_uniform, const double* density_host, double skip_below, double* total_out);
+int apply_dirichlet(toe_ctx* ctx, const int64_t* dofs, i64 nd, double* mean_out);
+int get_node_dofs(toe_ctx* ctx, int64_t* out_host);
+int get_cell_dofs(toe_ctx* ctx, i64 first, i64 count, int64_t* out_host);
+int get_pattern(toe_ctx* ctx, int64_t* colptr_host, int64_t* rowval_host);
+int get_values(toe_ctx* ctx, double* nzval_host);
+int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap);
+int time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out);
+int energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem_host);
+int energy_assembled(toe_ctx* ctx, double* half_uKu);
+int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell);
+int dist_comm_unique_id(char id_out[128], std::string& err);
+int dist_comm_init(toe_ctx* ctx, int nranks, int rank, const char id[128]);
+int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, const int64_t* conn);
+int dist_get_partition(toe_ctx* ctx, int32_t* part);
+int dist_local_sizes(toe_ctx* ctx, int64_t* ne_local, int64_t* ndofs_local, int64_t* nnz_local, int64_t* nif);
+int dist_gather_solution(toe_ctx* ctx, double* u_host);
+int dist_scatter_vector(toe_ctx* ctx, const double* global_host, double* local_dev);
+int dist_gather_vector(toe_ctx* ctx, const double* local_dev, double* global_host);
+bool dist_active(toe_ctx* ctx);
+
+static std::string g_create_error;
+static std::mutex g_mutex;
+
+#define GUARD(ctx) if (!(ctx)) return TOE_ERR_ARG; { cudaError_t _e = cudaSetDevice((ctx)->device); \
+    if (_e != cudaSuccess) return toe_fail((ctx), TOE_ERR_CUDA, "cudaSetDevice(%d): %s", (ctx)->device, cudaGetErrorString(_e)); }
+
+extern "C" {
+
+int toe_version(void) { return 100; }
+
+const char* toe_last_error(toe_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    return g_create_error.c_str();
+}
+
+int toe_create(int device, toe_ctx** out) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!out) return TOE_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libtopopt_b200 has no CPU fallback";
+        return TOE_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return TOE_ERR_ARG; }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return TOE_ERR_CUDA; }
+    if (prop.major != 10) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "device %d (%s) is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.name, prop.major, prop.minor);
+        g_create_error = buf;
+        return TOE_ERR_CUDA;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return TOE_ERR_CUDA; }
+    toe_ctx* c = new toe_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        g_create_error = "failed to create stream/events";
+        delete c;
+        return TOE_ERR_CUDA;
+    }
+    *out = c;
+    return TOE_OK;
+}
+
+void toe_destroy(toe_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    dist_destroy(ctx);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->cgs_host) cudaFreeHost(ctx->cgs_host);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    cudaStream_t s = ctx->stream;
+    delete ctx;                 // DevBuf destructors free device memory
+    if (s) cudaStreamDestroy(s);
+}
+
+int toe_get_timings(toe_ctx* ctx, toe_timings* out) {
+    if (!ctx || !out) return TOE_ERR_ARG;
+    *out = ctx->tm; out->kernel_launches = ctx->launches;
+    return TOE_OK;
+}
+
+int toe_set_mesh(toe_ctx* ctx, int64_t nn, const double* xyz, int64_t ne, int npc, const int64_t* conn) {
+    GUARD(ctx);
+    if (dist_active(ctx)) return toe_fail(ctx, TOE_ERR_STATE, "toe_set_mesh: this ctx has a communicator; use toe_set_mesh_distributed");
+    StageTimer T(ctx, &ctx->tm.set_mesh);
+    TRY(mesh_upload(ctx, nn, xyz, ne, npc, conn));
+    return T.finish();
+}
+
+int toe_build_dofs(toe_ctx* ctx, int64_t* ndofs_out) {
+    GUARD(ctx);
+    StageTimer T(ctx, &ctx->tm.build_dofs);
+    if (!ctx->have_dofs) TRY(mesh_build_dofs(ctx));
+    TRY(T.finish());
+    if (ndofs_out) *ndofs_out = 3 * (int64_t)ctx->nq;
+    return TOE_OK;
+}
+
+int toe_get_node_dofs(toe_ctx* ctx, int64_t* node_first_dof) { GUARD(ctx); if (!node_first_dof) return TOE_ERR_ARG; return get_node_dofs(ctx, node_first_dof); }
+int toe_get_cell_dofs(toe_ctx* ctx, int64_t first, int64_t count, int64_t* out) { GUARD(ctx); if (!out) return TOE_ERR_ARG; return get_cell_dofs(ctx, first, count, out); }
+
+int toe_build_pattern(toe_ctx* ctx, int64_t* nnz_out) {
+    GUARD(ctx);
+    StageTimer T(ctx, &ctx->tm.build_pattern);
+    if (!ctx->have_dofs) TRY(mesh_build_dofs(ctx));
+    if (!ctx->have_pattern) TRY(mesh_build_pattern(ctx));
+    TRY(T.finish());
+    if (nnz_out) *nnz_out = 9 * (int64_t)ctx->nnzb;
+    return TOE_OK;
+}
+
+int toe_get_pattern(toe_ctx* ctx, int64_t* colptr, int64_t* rowval) { GUARD(ctx); if (!colptr || !rowval) return TOE_ERR_ARG; return get_pattern(ctx, colptr, rowval); }
+
+static int set_material_common(toe_ctx* ctx) {
+    if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "material: call setup_problem (toe_build_dofs) first");
+    ctx->have_diag = false; ctx->have_solution = false;
+    ctx->op_generation++;
+    return TOE_OK;
+}
+
+static int set_lame(toe_ctx* ctx, double lambda, double mu) {
+    TRY(set_material_common(ctx));
+    ctx->mat = Material();
+    ctx->mat.mode = MAT_UNIFORM; ctx->mat.lambda = lambda; ctx->mat.mu = mu;
+    return TOE_OK;
+}
+
+static int set_simp(toe_ctx* ctx, double E0, double nu, double Emin, double p, const double* density) {
+    TRY(set_material_common(ctx));
+    if (!density) return toe_fail(ctx, TOE_ERR_ARG, "SIMP material needs a density vector");
+    CU(ctx->density.alloc(ctx->ne));
+    CU(cudaMemcpyAsync(ctx->density.p, density, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->mat = Material();
+    ctx->mat.mode = MAT_SIMP; ctx->mat.E0 = E0; ctx->mat.nu = nu; ctx->mat.Emin = Emin; ctx->mat.p = p;
+    ctx->mat.density = ctx->density.p;
+    return TOE_OK;
+}
+
+static int set_percell(toe_ctx* ctx, const double* lam, const double* mu) {
+    TRY(set_material_common(ctx));
+    if (!lam || !mu) return toe_fail(ctx, TOE_ERR_ARG, "per-cell material needs lambda and mu vectors");
+    CU(ctx->lam_e.alloc(ctx->ne)); CU(ctx->mu_e.alloc(ctx->ne));
+    CU(cudaMemcpyAsync(ctx->lam_e.p, lam, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->mu_e.p, mu, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->mat = Material();
+    ctx->mat.mode = MAT_PERCELL; ctx->mat.lam_e = ctx->lam_e.p; ctx->mat.mu_e = ctx->mu_e.p;
+    return TOE_OK;
+}
+
+// matrix-free path: same state change as an assembly (K and f zeroed, constraints dropped) without forming K
+static int reset_for_matrix_free(toe_ctx* ctx) {
+    TRY(ensure_vectors(ctx));
+    size_t n = 3 * (size_t)ctx->nq;
+    CU(cudaMemsetAsync(ctx->f.p, 0, n * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ctx->dflag.p, 0, n, ctx->stream));
+    CU(cudaMemsetAsync(ctx->dval.p, 0, n * sizeof(double), ctx->stream));
+    ctx->any_dirichlet = false; ctx->have_K = false;
+    return TOE_OK;
+}
+
+int toe_assemble_lame(toe_ctx* ctx, double lambda, double mu, int variant) {
+    GUARD(ctx); TRY(set_lame(ctx, lambda, mu)); return assemble_current_material(ctx, variant);
+}
+int toe_assemble_simp(toe_ctx* ctx, double E0, double nu, double Emin, double p, const double* density, int variant) {
+    GUARD(ctx); TRY(set_simp(ctx, E0, nu, Emin, p, density)); return assemble_current_material(ctx, variant);
+}
+int toe_assemble_lame_per_cell(toe_ctx* ctx, const double* lambda_e, const double* mu_e, int variant) {
+    GUARD(ctx); TRY(set_percell(ctx, lambda_e, mu_e)); return assemble_current_material(ctx, variant);
+}
+int toe_set_material_lame(toe_ctx* ctx, double lambda, double mu) {
+    GUARD(ctx); TRY(set_lame(ctx, lambda, mu)); return reset_for_matrix_free(ctx);
+}
+int toe_set_material_simp(toe_ctx* ctx, double E0, double nu, double Emin, double p, const double* density) {
+    GUARD(ctx); TRY(set_simp(ctx, E0, nu, Emin, p, density)); return reset_for_matrix_free(ctx);
+}
+
+int toe_ke_batch(toe_ctx* ctx, int64_t first, int64_t count, double* ke_out) { GUARD(ctx); if (!ke_out) return TOE_ERR_ARG; return ke_batch(ctx, first, count, ke_out); }
+int toe_get_values(toe_ctx* ctx, double* nzval) { GUARD(ctx); if (!nzval) return TOE_ERR_ARG; return get_values(ctx, nzval); }
+
+static int get_vec(toe_ctx* ctx, const double* dev, double* host) {
+    if (!host) return TOE_ERR_ARG;
+    if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "DOFs not built");
+    TRY(ensure_vectors(ctx));
+    if (dist_active(ctx)) return dist_gather_vector(ctx, dev, host);
+    CU(cudaMemcpyAsync(host, dev, 3 * (size_t)ctx->nq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TOE_OK;
+}
+static int set_vec(toe_ctx* ctx, const double* host, double* dev) {
+    if (!host) return TOE_ERR_ARG;
+    if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "DOFs not built");
+    TRY(ensure_vectors(ctx));
+    if (dist_active(ctx)) return dist_scatter_vector(ctx, host, dev);
+    CU(cudaMemcpyAsync(dev, host, 3 * (size_t)ctx->nq * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TOE_OK;
+}
+
+int toe_get_diagonal(toe_ctx* ctx, double* diag) { GUARD(ctx); TRY(compute_diag(ctx)); return get_vec(ctx, ctx->diag.p, diag); }
+int toe_get_rhs(toe_ctx* ctx, double* f) { GUARD(ctx); TRY(ensure_vectors(ctx)); return get_vec(ctx, ctx->f.p, f); }
+int toe_set_rhs(toe_ctx* ctx, const double* f) { GUARD(ctx); TRY(ensure_vectors(ctx)); ctx->have_solution = false; return set_vec(ctx, f, ctx->f.p); }
+int toe_get_solution(toe_ctx* ctx, double* u) { GUARD(ctx); TRY(ensure_vectors(ctx)); return get_vec(ctx, ctx->u.p, u); }
+int toe_set_solution(toe_ctx* ctx, const double* u) { GUARD(ctx); TRY(ensure_vectors(ctx)); TRY(set_vec(ctx, u, ctx->u.p)); ctx->have_solution = true; return TOE_OK; }
+
+int toe_add_nodal_force(toe_ctx* ctx, const int64_t* nodes, int64_t nnodes, const double F[3]) { GUARD(ctx); if (!F) return TOE_ERR_ARG; return add_nodal_force(ctx, nodes, nnodes, F); }
+int toe_add_volume_force(toe_ctx* ctx, const double b[3], double rho_uniform, const double* density, double skip_below, double* total_force_out) {
+    GUARD(ctx); if (!b) return TOE_ERR_ARG; return add_volume_force(ctx, b, rho_uniform, density, skip_below, total_force_out);
+}
+int toe_apply_dirichlet(toe_ctx* ctx, const int64_t* dofs, int64_t ndofs, double* mean_diag_out) { GUARD(ctx); return apply_dirichlet(ctx, dofs, ndofs, mean_diag_out); }
+
+int toe_solve_pcg(toe_ctx* ctx, double atol, double rtol, int64_t itmax, int flags, toe_pcg_stats* stats, double* history, int64_t history_cap) {
+    GUARD(ctx);
+    if (stats) memset(stats, 0, sizeof *stats);
+    return solve_pcg(ctx, atol, rtol, itmax, flags, stats, history, history_cap);
+}
+
+int toe_energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem) { GUARD(ctx); return energy(ctx, half_uKu, compliance, per_elem); }
+int toe_energy_assembled(toe_ctx* ctx, double* half_uKu) { GUARD(ctx); return energy_assembled(ctx, half_uKu); }
+int toe_stresses(toe_ctx* ctx, double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell) {
+    GUARD(ctx); return stresses(ctx, sigma, von_mises, max_von_mises, max_stress_cell);
+}
+
+int toe_spmv(toe_ctx* ctx, const double* x, double* y, int matrix_free) {
+    GUARD(ctx);
+    if (!x || !y) return TOE_ERR_ARG;
+    if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "DOFs not built");
+    TRY(ensure_vectors(ctx));
+    TRY(set_vec(ctx, x, ctx->r.p));
+    TRY(op_apply(ctx, ctx->r.p, ctx->tmp.p, matrix_free, nullptr, false));
+    return get_vec(ctx, ctx->tmp.p, y);
+}
+
+int toe_time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out) { GUARD(ctx); return time_spmv(ctx, matrix_free, reps, seconds_out, bytes_out); }
+
+int toe_comm_unique_id(char id_out[128]) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (!id_out) return TOE_ERR_ARG;
+    return dist_comm_unique_id(id_out, g_create_error);
+}
+int toe_comm_init(toe_ctx* ctx, int nranks, int rank, const char id[128]) { GUARD(ctx); if (!id) return TOE_ERR_ARG; return dist_comm_init(ctx, nranks, rank, id); }
+int toe_set_mesh_distributed(toe_ctx* ctx, int64_t nn, const double* xyz, int64_t ne, int npc, const int64_t* conn) {
+    GUARD(ctx);
+    StageTimer T(ctx, &ctx->tm.set_mesh);
+    TRY(dist_set_mesh(ctx, nn, xyz, ne, npc, conn));
+    return T.finish();
+}
+int toe_get_partition(toe_ctx* ctx, int32_t* part_of_cell) { GUARD(ctx); if (!part_of_cell) return TOE_ERR_ARG; return dist_get_partition(ctx, part_of_cell); }
+int toe_local_sizes(toe_ctx* ctx, int64_t* ne_local, int64_t* ndofs_local, int64_t* nnz_local, int64_t* n_interface_dofs) {
+    GUARD(ctx); return dist_local_sizes(ctx, ne_local, ndofs_local, nnz_local, n_interface_dofs);
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// common.cuh — context, device buffers, error plumbing and reduction helpers of libtopopt_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstdarg>
+
+#include "../../include/topopt_b200.h"
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+#define TOE_OK 0
+#define TOE_ERR_CUDA     -1
+#define TOE_ERR_ARG      -2
+#define TOE_ERR_STATE    -3
+#define TOE_ERR_MESH     -4
+#define TOE_ERR_COMM     -5
+#define TOE_ERR_NUMERIC  -6
+
+static const int N_SM = 148;   // B200: 2 dies x 74 SMs
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    cudaError_t resize_exact(size_t count) { release(); return alloc(count); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+enum MaterialMode { MAT_NONE = 0, MAT_UNIFORM = 1, MAT_SIMP = 2, MAT_PERCELL = 3 };
+
+// device-visible material description (passed by value to kernels)
+struct Material {
+    int mode;
+    double lambda, mu;            // MAT_UNIFORM
+    double E0, nu, Emin, p;       // MAT_SIMP
+    const double* density;        // MAT_SIMP (ne)
+    const double* lam_e;          // MAT_PERCELL
+    const double* mu_e;
+};
+
+// scalars of the PCG recurrence, resident on the device (no host round trip per iteration)
+struct CGScalars {
+    double gamma;      // r'z
+    double pAp;
+    double beta;
+    double eps;        // atol + rtol*sqrt(gamma0)
+    double res0;
+    double aux;        // scratch for extra reductions
+    i64 iter;
+    i64 itmax;
+    int done;
+    int converged;
+    int breakdown;
+    int pad;
+};
+
+struct DistState;   // dist.cu
+
+struct toe_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    toe_timings tm = {};
+    i64 launches = 0;
+
+    // mesh as given (global ids), sizes
+    i64 nn = 0, ne = 0;
+    int npc = 0;
+    bool have_mesh = false, have_dofs = false, have_pattern = false, have_contrib = false;
+    bool have_K = false, have_solution = false;
+
+    DevBuf<int> conn0;        // ne*npc, 0-based node ids (as given)
+    DevBuf<double> xyz;       // 3*nn as given
+    DevBuf<int> node_q;       // nn: dof-node id (first-touch rank) or -1
+    int nq = 0;               // number of referenced nodes; ndofs = 3*nq
+    DevBuf<int> cq;           // ne*npc connectivity in dof-node ids
+    DevBuf<double> xq;        // 3*nq coordinates in dof-node order
+    // node -> element incidence (entries e*npc+a, ascending)
+    DevBuf<int> inc_ptr, inc;
+    // block pattern (dof-node adjacency, sorted)
+    DevBuf<int> blk_ptr, blk_col, diag_slot;
+    i64 nnzb = 0;
+    // block -> contributing (e,a,b) lists, off-diagonal blocks only (entries e*64 + a*8 + b, ascending e)
+    DevBuf<int> ctr_ptr, ctr;
+    // K values: 9 planes of nnzb doubles, plane k = 3*c+d holds K[3q+c, 3q'+d] of block slot s at val[k*nnzb+s]
+    DevBuf<double> val;
+
+    // material
+    Material mat = {};
+    DevBuf<double> density, lam_e, mu_e;
+
+    // dof vectors
+    DevBuf<double> f, u, r, p, Ap, Minv, diag, tmp;
+    DevBuf<unsigned char> dflag;  // 1 = prescribed
+    DevBuf<double> dval;          // m of the handler that prescribed the dof (diag entry of the constrained K)
+    bool have_diag = false;       // diag holds diag of the current operator
+    bool any_dirichlet = false;
+
+    // reduction scratch
+    DevBuf<double> partials;
+    DevBuf<unsigned int> counters;
+    DevBuf<CGScalars> cgs;
+    DevBuf<double> hist;
+    DevBuf<int> errflag;
+
+    // CUDA graph of a batch of PCG iterations
+    cudaGraphExec_t graph_exec = nullptr;
+    i64 graph_key = -1;
+    i64 op_generation = 0;    // bumped whenever the operator (mesh, material, K, constraints) changes
+    CGScalars* cgs_host = nullptr;   // pinned readback buffer
+
+    DistState* dist = nullptr;
+};
+
+inline int toe_fail(toe_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) \
+    return toe_fail(ctx, TOE_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); } while (0)
+#define TRY(call) do { int _s = (call); if (_s != TOE_OK) return _s; } while (0)
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...) do { \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+
+static inline unsigned int div_up(i64 a, i64 b) { return (unsigned int)((a + b - 1) / b); }
+static inline unsigned int min_u(unsigned int a, unsigned int b) { return a < b ? a : b; }
+
+// ---- timing helper -------------------------------------------------------------------------------------
+struct StageTimer {
+    toe_ctx* c; double* slot;
+    StageTimer(toe_ctx* ctx, double* s) : c(ctx), slot(s) { cudaEventRecord(c->ev0, c->stream); }
+    int finish() {
+        cudaEventRecord(c->ev1, c->stream);
+        cudaError_t e = cudaEventSynchronize(c->ev1);
+        if (e != cudaSuccess) return toe_fail(c, TOE_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        *slot = ms * 1e-3;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return toe_fail(c, TOE_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+        return TOE_OK;
+    }
+};
+
+// ---- device reductions ---------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the block; result valid in thread 0.  `sh` must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    if (w == 0) {
+        v = lane < nw ? sh[lane] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+// Deterministic grid reduction: every block deposits its partial, the last block to arrive (ticket counter)
+// sums the partials in a fixed order.  Returns true in thread 0 of that last block, with *total set.
+// `partials` must hold gridDim.x doubles.
+__device__ __forceinline__ bool grid_sum_last_block(double block_val /*thread 0*/, double* partials, unsigned int* counter,
+                                                    double* sh, double* total) {
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = block_val;
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    double s = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) s += __ldcg(&partials[i]);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) { *total = s; *counter = 0u; return true; }
+    return false;
+}
+
+// (cell, a, b) packed into one int for the block -> contribution lists
+template <int NPC> __host__ __device__ __forceinline__ int ctr_pack(int e, int a, int b) {
+    return NPC == 4 ? ((e << 4) | (a << 2) | b) : ((e << 6) | (a << 3) | b);
+}
+template <int NPC> __host__ __device__ __forceinline__ void ctr_unpack(int v, int& e, int& a, int& b) {
+    if (NPC == 4) { e = v >> 4; a = (v >> 2) & 3; b = v & 3; } else { e = v >> 6; a = (v >> 3) & 7; b = v & 7; }
+}
+
+// ---- prototypes across translation units -----------------------------------------------------------------
+int scan_exclusive_i32(toe_ctx* ctx, const int* in, int* out, i64 n, i64* total_out);   // out may alias in; out has n+1 entries
+int mesh_upload(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, const int64_t* conn);
+int mesh_build_dofs(toe_ctx* ctx);
+int mesh_build_pattern(toe_ctx* ctx);
+int mesh_build_contrib(toe_ctx* ctx);
+int ensure_vectors(toe_ctx* ctx);
+int compute_diag(toe_ctx* ctx);   // diag of the current operator (assembled K or EbE + dirichlet overrides)
+int op_apply(toe_ctx* ctx, const double* x, double* y, int matrix_free, double* dot_out_dev /*or null*/, bool assume_masked);
+double op_bytes(toe_ctx* ctx, int matrix_free);
+int dist_post_spmv(toe_ctx* ctx, double* y);      // interface sum (no-op without dist)
+int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count);
+void dist_destroy(toe_ctx* ctx);

@@ -1,0 +1,650 @@
+// solver.cu — kernels (3)+(4) of the north star: Jacobi-preconditioned CG with an assembled block-CSR SpMV that
+// stages row products in shared memory, a matrix-free element-by-element operator, warp-shuffle dot products,
+// per-element strain energy, compliance and stress recovery.
+//
+// Reference loops replaced: Krylov.jl cg called at RobustSolver.jl:337 with the Jacobi preconditioner of :231-236;
+// energy lines FiniteElementAnalysis.jl:550 / :851, RobustSolver.jl:604 / :717; calculate_stresses :440-509 / :730-801.
+#include "element.cuh"
+#include <cmath>
+
+// ---------------------------------------------------------------------------------------------------------
+// PCG scalar recurrences (device side)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cg_after_pAp(CGScalars* s, double pAp) {
+    s->pAp = pAp;
+    if (!(pAp > 0.0)) { s->done = 1; s->breakdown = 1; }       // Krylov.jl stops on non-positive curvature
+}
+__device__ __forceinline__ void cg_after_gamma(CGScalars* s, double gnew, double* hist, i64 hist_cap) {
+    s->beta = gnew / s->gamma;
+    s->gamma = gnew;
+    s->iter += 1;
+    double res = sqrt(gnew);
+    if (s->iter < hist_cap) hist[s->iter] = res;
+    if (res <= s->eps) { s->done = 1; s->converged = 1; }
+    else if (s->iter >= s->itmax) s->done = 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// assembled operator: block-CSR SpMV.  A CTA owns SPMV_ROWS consecutive node rows (a contiguous range of block
+// slots).  Phase 1 streams the slots — thread t takes slot s0+t, s0+t+blockDim, … so the 9 value planes and the
+// column indices are read as fully coalesced streams — and leaves the three row products of each slot in shared
+// memory; phase 2 lets one thread per scalar row add up its staged segment.  The optional epilogue fuses the CG
+// dot product p'Ap.
+// ---------------------------------------------------------------------------------------------------------
+static const int SPMV_THREADS = 192;
+static const int SPMV_ROWS = 64;           // node rows per CTA → 192 scalar rows, one per thread in phase 2
+static const int SPMV_TILE = 1152;         // block slots staged per pass (6 per thread)
+
+template <bool CG>
+__global__ void __launch_bounds__(SPMV_THREADS) k_spmv_bsr(const int* __restrict__ blk_ptr, const int* __restrict__ blk_col,
+                                                           const double* __restrict__ val, i64 nnzb,
+                                                           const double* __restrict__ x, double* __restrict__ y, int nq,
+                                                           CGScalars* cg, double* partials, unsigned int* counter) {
+    __shared__ double prod[3][SPMV_TILE + 8];
+    __shared__ int sptr[SPMV_ROWS + 1];
+    __shared__ double red[32];
+    if (CG) { if (cg->done) return; }
+    const int t = threadIdx.x;
+    const int r0 = blockIdx.x * SPMV_ROWS;
+    const int nrows = min(SPMV_ROWS, nq - r0);
+    for (int i = t; i <= nrows; i += SPMV_THREADS) sptr[i] = __ldg(&blk_ptr[r0 + i]);
+    __syncthreads();
+    const int s0 = sptr[0], s1 = sptr[nrows];
+    const int lr = t / 3, c = t - 3 * lr;
+    const bool has_row = lr < nrows;
+    const int my_lo = has_row ? sptr[lr] : 0, my_hi = has_row ? sptr[lr + 1] : 0;
+    double acc = 0.0;
+    for (int base = s0; base < s1; base += SPMV_TILE) {
+        const int end = min(base + SPMV_TILE, s1);
+        for (int s = base + t; s < end; s += SPMV_THREADS) {
+            int col = __ldcs(&blk_col[s]);
+            const double* xp = x + 3 * (size_t)col;
+            double x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
+            const double* v = val + s;
+            double v0 = __ldcs(v), v1 = __ldcs(v + nnzb), v2 = __ldcs(v + 2 * nnzb);
+            double v3 = __ldcs(v + 3 * nnzb), v4 = __ldcs(v + 4 * nnzb), v5 = __ldcs(v + 5 * nnzb);
+            double v6 = __ldcs(v + 6 * nnzb), v7 = __ldcs(v + 7 * nnzb), v8 = __ldcs(v + 8 * nnzb);
+            int k = s - base;
+            prod[0][k] = v0 * x0 + v1 * x1 + v2 * x2;
+            prod[1][k] = v3 * x0 + v4 * x1 + v5 * x2;
+            prod[2][k] = v6 * x0 + v7 * x1 + v8 * x2;
+        }
+        __syncthreads();
+        int lo = max(my_lo, base), hi = min(my_hi, end);
+        for (int s = lo; s < hi; s++) acc += prod[c][s - base];
+        __syncthreads();
+    }
+    size_t row = 3 * (size_t)r0 + t;
+    if (has_row) y[row] = acc;
+    if (CG) {
+        double d = has_row ? acc * __ldg(&x[row]) : 0.0;
+        d = block_sum(d, red);
+        double tot;
+        if (grid_sum_last_block(d, partials, counter, red, &tot)) cg_after_pAp(cg, tot);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// matrix-free operator, gather form: one thread per node sums [Ke xe]_a over the cells of the node (ascending),
+// recomputing the element operator from the gradients held in registers — Ke is never formed:
+//   H = Σ_b x_b ⊗ g_b,  σ = λ tr(ε) I + 2μ ε,  y_a += w σ g_a
+// No atomics; deterministic.  Prescribed rows return m·x (constrained operator), prescribed columns are masked.
+// ---------------------------------------------------------------------------------------------------------
+template <int NPC, bool CG, bool MASK>
+__global__ void __launch_bounds__(128) k_ebe_gather(const int* __restrict__ inc_ptr, const int* __restrict__ inc, const int* __restrict__ cq,
+                                                    const double* __restrict__ xq, Material mat,
+                                                    const unsigned char* __restrict__ dflag, const double* __restrict__ dval, int any_dirichlet,
+                                                    const double* __restrict__ x, double* __restrict__ y, int nq,
+                                                    CGScalars* cg, double* partials, unsigned int* counter) {
+    __shared__ double red[32];
+    if (CG) { if (cg->done) return; }
+    int qn = blockIdx.x * blockDim.x + threadIdx.x;
+    double dotv = 0.0;
+    if (qn < nq) {
+        double ya[3] = {0, 0, 0};
+        int lo = __ldg(&inc_ptr[qn]), hi = __ldg(&inc_ptr[qn + 1]);
+        for (int i = lo; i < hi; i++) {
+            int ea = __ldg(&inc[i]);
+            int e = ea / NPC, a = ea - e * NPC;
+            double lam, mu; material_at(mat, e, lam, mu);
+            if (NPC == 4) {
+                int q[4]; double X[4][3], g[4][3];
+                tet_load(cq, xq, e, q, X);
+                double det = tet_grads(X, g);
+                double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    double xb[3]; load3(x, q[b], xb);
+                    if (MASK) {
+#pragma unroll
+                        for (int c2 = 0; c2 < 3; c2++) if (dflag[3 * (size_t)q[b] + c2]) xb[c2] = 0.0;
+                    }
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; c2++)
+#pragma unroll
+                        for (int i2 = 0; i2 < 3; i2++) H[c2][i2] += xb[c2] * g[b][i2];
+                }
+                double S[3][3]; hooke_from_grad(H, lam, mu, S);
+                double ga[3] = {g[0][0], g[0][1], g[0][2]};
+#pragma unroll
+                for (int k = 1; k < 4; k++) if (k == a) { ga[0] = g[k][0]; ga[1] = g[k][1]; ga[2] = g[k][2]; }
+                double w = det * (1.0 / 6.0);
+#pragma unroll
+                for (int c2 = 0; c2 < 3; c2++) ya[c2] += w * (S[c2][0] * ga[0] + S[c2][1] * ga[1] + S[c2][2] * ga[2]);
+            } else {
+                int q[8]; double X[8][3], xe[8][3];
+                hex_load(cq, xq, e, q, X);
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    load3(x, q[b], xe[b]);
+                    if (MASK) {
+#pragma unroll
+                        for (int c2 = 0; c2 < 3; c2++) if (dflag[3 * (size_t)q[b] + c2]) xe[b][c2] = 0.0;
+                    }
+                }
+                for (int gp = 0; gp < 8; gp++) {
+                    double g[8][3], N[8];
+                    double det = hex_grads_at(X, gp, g, N);
+                    double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+                    for (int b = 0; b < 8; b++)
+#pragma unroll
+                        for (int c2 = 0; c2 < 3; c2++)
+#pragma unroll
+                            for (int i2 = 0; i2 < 3; i2++) H[c2][i2] += xe[b][c2] * g[b][i2];
+                    double S[3][3]; hooke_from_grad(H, lam, mu, S);
+                    double ga[3] = {g[0][0], g[0][1], g[0][2]};
+#pragma unroll
+                    for (int k = 1; k < 8; k++) if (k == a) { ga[0] = g[k][0]; ga[1] = g[k][1]; ga[2] = g[k][2]; }
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; c2++) ya[c2] += det * (S[c2][0] * ga[0] + S[c2][1] * ga[1] + S[c2][2] * ga[2]);
+                }
+            }
+        }
+        double xs[3]; load3(x, qn, xs);
+        if (any_dirichlet) {
+#pragma unroll
+            for (int c2 = 0; c2 < 3; c2++) { size_t d = 3 * (size_t)qn + c2; if (dflag[d]) ya[c2] = dval[d] * xs[c2]; }
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < 3; c2++) y[3 * (size_t)qn + c2] = ya[c2];
+        dotv = ya[0] * xs[0] + ya[1] * xs[1] + ya[2] * xs[2];
+    }
+    if (CG) {
+        double d = block_sum(dotv, red);
+        double tot;
+        if (grid_sum_last_block(d, partials, counter, red, &tot)) cg_after_pAp(cg, tot);
+    }
+}
+
+double op_bytes(toe_ctx* ctx, int matrix_free) {
+    double n = 3.0 * ctx->nq;
+    if (matrix_free)   // conn + material per cell, coordinates per node, x read + y write
+        return (double)ctx->ne * (4.0 * ctx->npc + 8.0) + ctx->nq * 24.0 + n * 16.0;
+    // block-CSR: 8 B per value + 4 B per 3x3 block index + row pointers + x read + y write
+    return 9.0 * ctx->nnzb * 8.0 + ctx->nnzb * 4.0 + (ctx->nq + 1) * 4.0 + n * 16.0;
+}
+
+// y = A x.  cg != null: PCG mode (early exit on cg->done, fused p'Ap).  assume_masked: x is zero on prescribed dofs.
+static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, CGScalars* cg, bool assume_masked) {
+    if (!matrix_free) {
+        if (!ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "assembled operator requested but K is not assembled");
+        unsigned grid = div_up(ctx->nq, SPMV_ROWS);
+        if (cg) LAUNCH(ctx, k_spmv_bsr<true>, grid, SPMV_THREADS, 0, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
+                       ctx->nnzb, x, y, ctx->nq, cg, ctx->partials.p, ctx->counters.p + 1);
+        else    LAUNCH(ctx, k_spmv_bsr<false>, grid, SPMV_THREADS, 0, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
+                       ctx->nnzb, x, y, ctx->nq, (CGScalars*)nullptr, (double*)nullptr, (unsigned int*)nullptr);
+        return TOE_OK;
+    }
+    if (ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "matrix-free operator requested but no material is set");
+    if (!ctx->have_pattern) return toe_fail(ctx, TOE_ERR_STATE, "matrix-free operator needs the incidence lists (toe_build_pattern)");
+    unsigned grid = div_up(ctx->nq, 128);
+    bool mask = ctx->any_dirichlet && !assume_masked;
+#define EBE_ARGS (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, \
+        (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, (int)ctx->any_dirichlet, x, y, ctx->nq, cg, ctx->partials.p, ctx->counters.p + 1
+    if (ctx->npc == 4) {
+        if (cg) { if (mask) LAUNCH(ctx, (k_ebe_gather<4, true, true>), grid, 128, 0, EBE_ARGS); else LAUNCH(ctx, (k_ebe_gather<4, true, false>), grid, 128, 0, EBE_ARGS); }
+        else    { if (mask) LAUNCH(ctx, (k_ebe_gather<4, false, true>), grid, 128, 0, EBE_ARGS); else LAUNCH(ctx, (k_ebe_gather<4, false, false>), grid, 128, 0, EBE_ARGS); }
+    } else {
+        if (cg) { if (mask) LAUNCH(ctx, (k_ebe_gather<8, true, true>), grid, 128, 0, EBE_ARGS); else LAUNCH(ctx, (k_ebe_gather<8, true, false>), grid, 128, 0, EBE_ARGS); }
+        else    { if (mask) LAUNCH(ctx, (k_ebe_gather<8, false, true>), grid, 128, 0, EBE_ARGS); else LAUNCH(ctx, (k_ebe_gather<8, false, false>), grid, 128, 0, EBE_ARGS); }
+    }
+#undef EBE_ARGS
+    return TOE_OK;
+}
+
+int op_apply(toe_ctx* ctx, const double* x, double* y, int matrix_free, double* /*unused*/, bool assume_masked) {
+    TRY(op_launch(ctx, x, y, matrix_free, nullptr, assume_masked));
+    return dist_post_spmv(ctx, y);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PCG vector kernels
+// ---------------------------------------------------------------------------------------------------------
+static const int VEC_THREADS = 256;
+static unsigned vec_grid(size_t n) { return min_u(div_up((i64)n, VEC_THREADS), (unsigned)(N_SM * 8)); }
+
+// x = 0, r = f, Minv = 1 ./ D with D[abs(D) < 1e-12] = 1 (RobustSolver.jl:231-236), z = M r, p = z, γ = r'z
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_init(const double* __restrict__ f, const double* __restrict__ diag, double* __restrict__ Minv,
+                                                         double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, size_t n,
+                                                         CGScalars* cg, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap,
+                                                         double* partials, unsigned int* counter) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double d = diag[i];
+        if (fabs(d) < 1e-12) d = 1.0;
+        double mi = 1.0 / d, ri = f[i], zi = mi * ri;
+        Minv[i] = mi; x[i] = 0.0; r[i] = ri; p[i] = zi;
+        s += ri * zi;
+    }
+    s = block_sum(s, red);
+    double tot;
+    if (grid_sum_last_block(s, partials, counter, red, &tot)) {
+        cg->gamma = tot; cg->pAp = 0.0; cg->beta = 0.0;
+        cg->res0 = sqrt(tot);
+        cg->eps = atol + rtol * cg->res0;
+        cg->iter = 0; cg->itmax = itmax;
+        cg->converged = (cg->res0 <= cg->eps) ? 1 : 0;
+        cg->done = (cg->converged || itmax <= 0) ? 1 : 0;
+        cg->breakdown = 0;
+        if (hist_cap > 0) hist[0] = cg->res0;
+    }
+}
+
+// α = γ/p'Ap, x += α p, r -= α Ap, γ' = r' M r; the last block closes the iteration (β, convergence test)
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_xr(const double* __restrict__ p, const double* __restrict__ Ap, const double* __restrict__ Minv,
+                                                       double* __restrict__ x, double* __restrict__ r, size_t n, CGScalars* cg,
+                                                       double* hist, i64 hist_cap, double* partials, unsigned int* counter) {
+    __shared__ double red[32];
+    if (cg->done) return;
+    const double alpha = cg->gamma / cg->pAp;
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double pi = p[i];
+        x[i] += alpha * pi;
+        double ri = r[i] - alpha * Ap[i];
+        r[i] = ri;
+        s += ri * ri * Minv[i];
+    }
+    s = block_sum(s, red);
+    double tot;
+    if (grid_sum_last_block(s, partials, counter, red, &tot)) cg_after_gamma(cg, tot, hist, hist_cap);
+}
+
+// p = M r + β p
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_p(const double* __restrict__ r, const double* __restrict__ Minv, double* __restrict__ p,
+                                                      size_t n, const CGScalars* cg) {
+    if (cg->done) return;
+    const double beta = cg->beta;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = Minv[i] * r[i] + beta * p[i];
+}
+
+// out[0] = Σ (a-b)^2, out[1] = Σ a^2, out[2] = Σ a*b
+__global__ void __launch_bounds__(VEC_THREADS) k_norms(const double* __restrict__ a, const double* __restrict__ b, size_t n, double* out,
+                                                       double* partials, unsigned int* counter) {
+    __shared__ double red[32];
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double ai = a[i], bi = b[i], d = ai - bi;
+        s0 += d * d; s1 += ai * ai; s2 += ai * bi;
+    }
+    double tot;
+    s0 = block_sum(s0, red);
+    if (grid_sum_last_block(s0, partials, counter, red, &tot)) out[0] = tot;
+    s1 = block_sum(s1, red);
+    if (grid_sum_last_block(s1, partials + gridDim.x, counter + 1, red, &tot)) out[1] = tot;
+    s2 = block_sum(s2, red);
+    if (grid_sum_last_block(s2, partials + 2 * gridDim.x, counter + 2, red, &tot)) out[2] = tot;
+}
+
+static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap) {
+    TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, ctx->cgs.p, true));
+    LAUNCH(ctx, k_cg_xr, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p,
+           ctx->u.p, ctx->r.p, n, ctx->cgs.p, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p + 2);
+    LAUNCH(ctx, k_cg_p, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->Minv.p, ctx->p.p, n, (const CGScalars*)ctx->cgs.p);
+    return TOE_OK;
+}
+
+int solve_pcg_dist(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap);  // dist.cu
+
+static const int CG_BATCH = 50;
+static const i64 HIST_CAP = 1LL << 20;
+
+int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap) {
+    if (ctx->dist) return solve_pcg_dist(ctx, atol, rtol, itmax, flags, stats, history, history_cap);
+    int matrix_free = (flags & TOE_PCG_MATRIX_FREE) ? 1 : 0;
+    if (!matrix_free && !ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "solve: K is not assembled (or pass TOE_PCG_MATRIX_FREE)");
+    if (matrix_free && ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "solve: no material set");
+    if (itmax < 0) return toe_fail(ctx, TOE_ERR_ARG, "solve: itmax must be >= 0");
+    TRY(ensure_vectors(ctx));
+    TRY(compute_diag(ctx));
+    size_t n = 3 * (size_t)ctx->nq;
+    const i64 hist_cap = HIST_CAP;            // fixed: pointer and capacity are baked into the captured graph
+    CU(ctx->hist.alloc(hist_cap));
+    if (!ctx->cgs_host) CU(cudaMallocHost((void**)&ctx->cgs_host, sizeof(CGScalars)));
+    i64 launches0 = ctx->launches;
+
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, ctx->stream));
+    LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
+           ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p);
+
+    bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
+    i64 key = ctx->op_generation * 4 + matrix_free * 2 + 1;
+    if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
+        if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        i64 l0 = ctx->launches;
+        int st = TOE_OK;
+        for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = cg_iteration(ctx, matrix_free, n, hist_cap);
+        ctx->launches = l0;
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        if (st != TOE_OK) { if (g) cudaGraphDestroy(g); return st; }
+        if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        ctx->graph_key = key;
+    }
+    i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
+    for (i64 bt = 0; bt < max_batches; bt++) {
+        if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += 3 * CG_BATCH; }
+        else for (int k = 0; k < CG_BATCH; k++) TRY(cg_iteration(ctx, matrix_free, n, hist_cap));
+        CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->cgs_host->done) break;
+    }
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CU(cudaGetLastError());
+    CGScalars h = *ctx->cgs_host;
+    ctx->tm.solve = ms * 1e-3;
+    ctx->have_solution = true;
+
+    if (stats) {
+        stats->niter = h.iter; stats->converged = h.converged; stats->breakdown = h.breakdown;
+        stats->res0_M = h.res0; stats->res_M = sqrt(h.gamma);
+        stats->solve_seconds = ms * 1e-3;
+        // true residual ||f - K u|| / ||f||  (RobustSolver.jl:468)
+        TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
+        double* out = ctx->partials.p + 3 * (N_SM * 8) + 8;
+        LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->tmp.p, n, out, ctx->partials.p, ctx->counters.p + 4);
+        double hn[3];
+        CU(cudaMemcpyAsync(hn, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        stats->rel_res_l2 = hn[1] > 0 ? sqrt(hn[0] / hn[1]) : sqrt(hn[0]);
+        // operator time: a few isolated launches
+        const int reps = 5;
+        cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+        TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
+        CU(cudaEventRecord(a, ctx->stream));
+        for (int k = 0; k < reps; k++) TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
+        CU(cudaEventRecord(b, ctx->stream));
+        CU(cudaEventSynchronize(b));
+        float oms = 0; cudaEventElapsedTime(&oms, a, b);
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        stats->spmv_seconds = (double)h.iter * (oms * 1e-3 / reps);
+        stats->spmv_bytes = op_bytes(ctx, matrix_free);
+        stats->kernel_launches = ctx->launches - launches0;
+    }
+    if (history && history_cap > 0) {
+        i64 cnt = h.iter + 1 < history_cap ? h.iter + 1 : history_cap;
+        if (cnt > hist_cap) cnt = hist_cap;
+        CU(cudaMemcpy(history, ctx->hist.p, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return TOE_OK;
+}
+
+int time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out) {
+    TRY(ensure_vectors(ctx));
+    if (reps < 1) reps = 1;
+    cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, false));
+    CU(cudaEventRecord(a, ctx->stream));
+    for (int k = 0; k < reps; k++) TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, false));
+    CU(cudaEventRecord(b, ctx->stream));
+    CU(cudaEventSynchronize(b));
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    CU(cudaGetLastError());
+    if (seconds_out) *seconds_out = ms * 1e-3 / reps;
+    if (bytes_out) *bytes_out = op_bytes(ctx, matrix_free);
+    return TOE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// energy: eₑ = ½ uₑᵀ Kₑ uₑ = ½ Σ_q (λ tr(ε)² + 2μ ε:ε) dΩ, Σ eₑ, compliance f'u
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double strain_energy_density(const double H[3][3], double lam, double mu) {
+    double tr = H[0][0] + H[1][1] + H[2][2];
+    double exy = 0.5 * (H[0][1] + H[1][0]), eyz = 0.5 * (H[1][2] + H[2][1]), exz = 0.5 * (H[0][2] + H[2][0]);
+    double ee = H[0][0] * H[0][0] + H[1][1] * H[1][1] + H[2][2] * H[2][2] + 2.0 * (exy * exy + eyz * eyz + exz * exz);
+    return 0.5 * (lam * tr * tr + 2.0 * mu * ee);
+}
+
+template <int NPC>
+__global__ void __launch_bounds__(128) k_elem_energy(const int* __restrict__ cq, const double* __restrict__ xq, Material mat,
+                                                     const double* __restrict__ u, double* __restrict__ ee_out, int ne,
+                                                     double* partials) {
+    __shared__ double red[32];
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double en = 0.0;
+    if (e < ne) {
+        double lam, mu; material_at(mat, e, lam, mu);
+        if (NPC == 4) {
+            int q[4]; double X[4][3], g[4][3];
+            tet_load(cq, xq, e, q, X);
+            double det = tet_grads(X, g);
+            double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                double ub[3]; load3(u, q[b], ub);
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int i = 0; i < 3; i++) H[c][i] += ub[c] * g[b][i];
+            }
+            en = strain_energy_density(H, lam, mu) * det * (1.0 / 6.0);
+        } else {
+            int q[8]; double X[8][3], ue[8][3];
+            hex_load(cq, xq, e, q, X);
+#pragma unroll
+            for (int b = 0; b < 8; b++) load3(u, q[b], ue[b]);
+            for (int gp = 0; gp < 8; gp++) {
+                double g[8][3], N[8];
+                double det = hex_grads_at(X, gp, g, N);
+                double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+                for (int b = 0; b < 8; b++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+#pragma unroll
+                        for (int i = 0; i < 3; i++) H[c][i] += ue[b][c] * g[b][i];
+                en += strain_energy_density(H, lam, mu) * det;
+            }
+        }
+        if (ee_out) ee_out[e] = en;
+    }
+    double s = block_sum(en, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// fixed-order two-level sum of n partials (n may exceed one block's reach)
+__global__ void k_sum_strided(const double* __restrict__ in, i64 n, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (i64 i = threadIdx.x; i < n; i += blockDim.x) s += in[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) *out = s;
+}
+
+int energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem_host) {
+    if (!ctx->have_dofs || ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "energy: mesh/material not set");
+    TRY(ensure_vectors(ctx));
+    size_t n = 3 * (size_t)ctx->nq;
+    int ne = (int)ctx->ne;
+    StageTimer T(ctx, &ctx->tm.energy);
+    unsigned grid = div_up(ne, 128);
+    DevBuf<double> part; CU(part.alloc(grid + 4));
+    DevBuf<double> ee;
+    if (per_elem_host) CU(ee.alloc(ne));
+    double* eep = per_elem_host ? ee.p : nullptr;
+    if (ctx->npc == 4) LAUNCH(ctx, k_elem_energy<4>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, (const double*)ctx->u.p, eep, ne, part.p);
+    else               LAUNCH(ctx, k_elem_energy<8>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, (const double*)ctx->u.p, eep, ne, part.p);
+    LAUNCH(ctx, k_sum_strided, 1, 1024, 0, (const double*)part.p, (i64)grid, part.p + grid);
+    double* out = ctx->partials.p + 3 * (N_SM * 8) + 8;
+    LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->u.p, n, out, ctx->partials.p, ctx->counters.p + 4);
+    TRY(dist_allreduce(ctx, part.p + grid, 1));
+    double h_e = 0, hn[3];
+    CU(cudaMemcpyAsync(&h_e, part.p + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hn, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (per_elem_host) CU(cudaMemcpyAsync(per_elem_host, ee.p, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(T.finish());
+    if (half_uKu) *half_uKu = h_e;
+    if (compliance) *compliance = hn[2];
+    return TOE_OK;
+}
+
+int energy_assembled(toe_ctx* ctx, double* half_uKu) {
+    if (!ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "energy_assembled: K not assembled");
+    TRY(ensure_vectors(ctx));
+    size_t n = 3 * (size_t)ctx->nq;
+    TRY(op_apply(ctx, ctx->u.p, ctx->tmp.p, 0, nullptr, false));
+    double* out = ctx->partials.p + 3 * (N_SM * 8) + 8;
+    LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->u.p, (const double*)ctx->tmp.p, n, out, ctx->partials.p, ctx->counters.p + 4);
+    double hn[3];
+    CU(cudaMemcpyAsync(hn, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (half_uKu) *half_uKu = 0.5 * hn[2];
+    return TOE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stress recovery (calculate_stresses, FiniteElementAnalysis.jl:440-509 / :730-801)
+// ---------------------------------------------------------------------------------------------------------
+template <int NPC>
+__global__ void __launch_bounds__(128) k_stress(const int* __restrict__ cq, const double* __restrict__ xq, Material mat,
+                                                const double* __restrict__ u, double* __restrict__ sigma, double* __restrict__ vm_out, int ne,
+                                                double* __restrict__ bmax, int* __restrict__ barg) {
+    const int NQ = NPC == 4 ? 4 : 8;
+    __shared__ double smax[128];
+    __shared__ int sarg[128];
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double vm = -1.0;
+    if (e < ne) {
+        double lam, mu; material_at(mat, e, lam, mu);
+        double avg[6] = {0, 0, 0, 0, 0, 0};
+        if (NPC == 4) {
+            int q[4]; double X[4][3], g[4][3];
+            tet_load(cq, xq, e, q, X);
+            tet_grads(X, g);
+            double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                double ub[3]; load3(u, q[b], ub);
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int i = 0; i < 3; i++) H[c][i] += ub[c] * g[b][i];
+            }
+            double S[3][3]; hooke_from_grad(H, lam, mu, S);
+            double s6[6] = {S[0][0], S[1][1], S[2][2], S[0][1], S[1][2], S[0][2]};
+            for (int gp = 0; gp < NQ; gp++) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) { if (sigma) sigma[((size_t)e * NQ + gp) * 6 + k] = s6[k]; avg[k] += s6[k]; }
+            }
+        } else {
+            int q[8]; double X[8][3], ue[8][3];
+            hex_load(cq, xq, e, q, X);
+#pragma unroll
+            for (int b = 0; b < 8; b++) load3(u, q[b], ue[b]);
+            for (int gp = 0; gp < 8; gp++) {
+                double g[8][3], N[8];
+                hex_grads_at(X, gp, g, N);
+                double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+                for (int b = 0; b < 8; b++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+#pragma unroll
+                        for (int i = 0; i < 3; i++) H[c][i] += ue[b][c] * g[b][i];
+                double S[3][3]; hooke_from_grad(H, lam, mu, S);
+                double s6[6] = {S[0][0], S[1][1], S[2][2], S[0][1], S[1][2], S[0][2]};
+#pragma unroll
+                for (int k = 0; k < 6; k++) { if (sigma) sigma[((size_t)e * NQ + gp) * 6 + k] = s6[k]; avg[k] += s6[k]; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) avg[k] /= (double)NQ;
+        // sqrt(3/2 dev(σ)⊡dev(σ))
+        double mean = (avg[0] + avg[1] + avg[2]) / 3.0;
+        double d0 = avg[0] - mean, d1 = avg[1] - mean, d2 = avg[2] - mean;
+        double dd = d0 * d0 + d1 * d1 + d2 * d2 + 2.0 * (avg[3] * avg[3] + avg[4] * avg[4] + avg[5] * avg[5]);
+        vm = sqrt(1.5 * dd);
+        if (vm_out) vm_out[e] = vm;
+    }
+    // block arg-max, first maximum wins (strict `>` in the reference loop, :492)
+    smax[threadIdx.x] = vm; sarg[threadIdx.x] = e;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double v2 = smax[threadIdx.x + o]; int a2 = sarg[threadIdx.x + o];
+            if (v2 > smax[threadIdx.x] || (v2 == smax[threadIdx.x] && a2 < sarg[threadIdx.x])) { smax[threadIdx.x] = v2; sarg[threadIdx.x] = a2; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { bmax[blockIdx.x] = smax[0]; barg[blockIdx.x] = sarg[0]; }
+}
+
+__global__ void k_argmax_final(const double* __restrict__ bmax, const int* __restrict__ barg, int n, double* omax, int* oarg) {
+    __shared__ double smax[1024];
+    __shared__ int sarg[1024];
+    double v = -1.0; int a = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v2 = bmax[i]; int a2 = barg[i];
+        if (v2 > v || (v2 == v && a2 < a)) { v = v2; a = a2; }
+    }
+    smax[threadIdx.x] = v; sarg[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            double v2 = smax[threadIdx.x + o]; int a2 = sarg[threadIdx.x + o];
+            if (v2 > smax[threadIdx.x] || (v2 == smax[threadIdx.x] && a2 < sarg[threadIdx.x])) { smax[threadIdx.x] = v2; sarg[threadIdx.x] = a2; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *omax = smax[0]; *oarg = sarg[0]; }
+}
+
+int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell) {
+    if (!ctx->have_dofs || ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "stresses: mesh/material not set");
+    TRY(ensure_vectors(ctx));
+    int ne = (int)ctx->ne;
+    int nqp = ctx->npc == 4 ? 4 : 8;
+    unsigned grid = div_up(ne, 128);
+    DevBuf<double> sig, vm, bmax; DevBuf<int> barg;
+    if (sigma_host) CU(sig.alloc((size_t)ne * nqp * 6));
+    if (vm_host) CU(vm.alloc(ne));
+    CU(bmax.alloc(grid + 1)); CU(barg.alloc(grid + 1));
+    double* sp = sigma_host ? sig.p : nullptr; double* vp = vm_host ? vm.p : nullptr;
+    if (ctx->npc == 4) LAUNCH(ctx, k_stress<4>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, (const double*)ctx->u.p, sp, vp, ne, bmax.p, barg.p);
+    else               LAUNCH(ctx, k_stress<8>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, (const double*)ctx->u.p, sp, vp, ne, bmax.p, barg.p);
+    LAUNCH(ctx, k_argmax_final, 1, 1024, 0, (const double*)bmax.p, (const int*)barg.p, (int)grid, bmax.p + grid, barg.p + grid);
+    double hm = 0; int ha = 0;
+    CU(cudaMemcpyAsync(&hm, bmax.p + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ha, barg.p + grid, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sigma_host) CU(cudaMemcpyAsync(sigma_host, sig.p, (size_t)ne * nqp * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (vm_host) CU(cudaMemcpyAsync(vm_host, vm.p, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    // reference semantics: max starts at 0.0 and cell id 0, updated only on strict > (:446-447, :492)
+    if (hm > 0.0) { if (max_vm) *max_vm = hm; if (max_cell) *max_cell = (int64_t)ha + 1; }
+    else { if (max_vm) *max_vm = 0.0; if (max_cell) *max_cell = 0; }
+    return TOE_OK;
+}
