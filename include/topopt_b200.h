@@ -64,6 +64,9 @@ int         toe_create(int device, toe_ctx** out);
 void        toe_destroy(toe_ctx* ctx);
 const char* toe_last_error(toe_ctx* ctx);            /* ctx may be NULL: error of the last failed toe_create */
 int         toe_get_timings(toe_ctx* ctx, toe_timings* out);
+/* device stopwatch on the ctx's own stream (CUDA events): what bench.py brackets its timed region with */
+int         toe_timer_start(toe_ctx* ctx);
+int         toe_timer_stop(toe_ctx* ctx, double* seconds_out);
 
 /* ---- setup_problem (FiniteElementAnalysis.jl:151-185) ------------------------------------------------ */
 /* xyz: 3*nn doubles, node-major (= Julia 3×nn column-major, grid.nodes); conn: npc*ne int64, 1-based,

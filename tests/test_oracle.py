@@ -96,3 +96,37 @@ def test_gravity_cantilever_known_answer(fo, pkg):
     analytic = rho * g * L ** 4 / (8 * E * (h ** 4 / 12))
     assert abs(analytic - 5.7756375e-3) < 1e-9
     assert abs(defl - analytic) / analytic < 0.10
+
+
+def test_c_oracle_agrees_with_numpy_oracle(fo, pkg, golden_c1):
+    """The C restatement (timed CPU baseline) and the numpy restatement are independent: they must agree."""
+    from oracle import c_oracle
+    pts, cells = golden_c1["points"], golden_c1["cells"].astype(np.int64)
+    cp = c_oracle.CProblem(pts, cells)
+    prob = fo.setup_problem(pts, cells)
+    assert cp.n == prob.ndofs and cp.nnz == prob.nnz
+    assert np.array_equal(cp.node_first_dof + 1, prob.node_first_dof)
+    assert np.array_equal(cp.colptr + 1, prob.colptr) and np.array_equal(cp.rowval + 1, prob.rowval)
+    lam, mu = fo.create_material_model(1.0, 0.3)
+    ke_c = cp.ke_batch(0, 32, lam_mu=(lam, mu))
+    ke_n = fo.element_stiffness(pts, cells[:32], lam, mu)
+    assert np.max(np.abs(ke_c - ke_n)) <= 1e-13 * np.abs(ke_n).max()
+    cp.assemble(lam_mu=(lam, mu)); fo.assemble_stiffness_matrix(prob, lam, mu)
+    assert np.max(np.abs(cp.nzval - prob.nzval)) <= 1e-13 * np.abs(prob.nzval).max()
+    cp.apply_force(golden_c1["load_nodes"], [0, 0, -1.0])
+    m = cp.apply_dirichlet(golden_c1["prescribed"] - 1)
+    assert abs(m - float(golden_c1["mean_diag"])) < 1e-12
+    x, k, solved, res = cp.pcg(1e-8, 20000, history=True)
+    assert solved and abs(k - int(golden_c1["pcg_niter"])) <= 20
+    assert np.linalg.norm(x - golden_c1["u"]) <= 1e-8 * np.linalg.norm(golden_c1["u"])
+    assert abs(cp.energy(x) - float(golden_c1["energy"])) <= 1e-8 * float(golden_c1["energy"])
+
+
+def test_c_oracle_hex_simp(fo, golden_c2):
+    from oracle import c_oracle
+    pts, cells, rho = golden_c2["points"], golden_c2["cells"].astype(np.int64), golden_c2["density"]
+    cp = c_oracle.CProblem(pts, cells)
+    ke_c = cp.ke_batch(100, 8, simp=(1.0, 0.3, 1e-8, 3.0), density=rho)
+    lam, mu = fo.create_simp_material_model(1.0, 0.3, 1e-8, 3.0)(rho)
+    ke_n = fo.element_stiffness(pts, cells[100:108], lam[100:108], mu[100:108])
+    assert np.max(np.abs(ke_c - ke_n)) <= 1e-13 * np.abs(ke_n).max()

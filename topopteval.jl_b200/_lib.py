@@ -50,6 +50,8 @@ SIGNATURES = {
     "toe_destroy": (None, [_P]),
     "toe_last_error": (C.c_char_p, [_P]),
     "toe_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
+    "toe_timer_start": (C.c_int, [_P]),
+    "toe_timer_stop": (C.c_int, [_P, _D]),
     "toe_set_mesh": (C.c_int, [_P, C.c_int64, _D, C.c_int64, C.c_int, _I64]),
     "toe_build_dofs": (C.c_int, [_P, _I64]),
     "toe_get_node_dofs": (C.c_int, [_P, _I64]),
@@ -312,6 +314,14 @@ class Context:
         s = C.c_double(); b = C.c_double()
         self._ck(self.lib.toe_time_spmv(self.h, 1 if matrix_free else 0, reps, C.byref(s), C.byref(b)))
         return s.value, b.value
+
+    def timer_start(self):
+        self._ck(self.lib.toe_timer_start(self.h))
+
+    def timer_stop(self):
+        s = C.c_double()
+        self._ck(self.lib.toe_timer_stop(self.h, C.byref(s)))
+        return s.value
 
     def timings(self):
         t = Timings()

@@ -87,6 +87,8 @@ void toe_destroy(toe_ctx* ctx) {
     if (ctx->cgs_host) cudaFreeHost(ctx->cgs_host);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     cudaStream_t s = ctx->stream;
     delete ctx;                 // DevBuf destructors free device memory
     if (s) cudaStreamDestroy(s);
@@ -95,6 +97,23 @@ void toe_destroy(toe_ctx* ctx) {
 int toe_get_timings(toe_ctx* ctx, toe_timings* out) {
     if (!ctx || !out) return TOE_ERR_ARG;
     *out = ctx->tm; out->kernel_launches = ctx->launches;
+    return TOE_OK;
+}
+
+int toe_timer_start(toe_ctx* ctx) {
+    GUARD(ctx);
+    if (!ctx->ev_t0) { CU(cudaEventCreate(&ctx->ev_t0)); CU(cudaEventCreate(&ctx->ev_t1)); }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return TOE_OK;
+}
+int toe_timer_stop(toe_ctx* ctx, double* seconds_out) {
+    GUARD(ctx);
+    if (!ctx->ev_t0) return toe_fail(ctx, TOE_ERR_STATE, "toe_timer_stop without toe_timer_start");
+    CU(cudaEventRecord(ctx->ev_t1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev_t1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+    if (seconds_out) *seconds_out = ms * 1e-3;
     return TOE_OK;
 }
 

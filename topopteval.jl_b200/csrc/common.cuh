@@ -77,7 +77,7 @@ struct toe_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     toe_timings tm = {};
     i64 launches = 0;
 
