@@ -186,7 +186,7 @@ __global__ void k_asm_atomic_hex(const int* __restrict__ cq, const double* __res
 template <int NPC>
 __global__ void __launch_bounds__(128) k_asm_offdiag(const int* __restrict__ ctr_ptr, const int* __restrict__ ctr,
                                                      const int* __restrict__ cq, const double* __restrict__ xq, Material mat,
-                                                     double* __restrict__ val, i64 nnzb) {
+                                                     double* __restrict__ val, i64 nnzb, i64 ldv) {
     i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nnzb) return;
     int lo = __ldg(&ctr_ptr[s]), hi = __ldg(&ctr_ptr[s + 1]);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(128) k_asm_offdiag(const int* __restrict__ ctr
         }
     }
 #pragma unroll
-    for (int k = 0; k < 9; k++) val[(size_t)k * nnzb + s] = acc[k];
+    for (int k = 0; k < 9; k++) val[(size_t)k * ldv + s] = acc[k];
 }
 
 template <int NPC>
@@ -276,8 +276,11 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
     if (variant != TOE_ASM_ATOMIC && variant != TOE_ASM_GATHER) return toe_fail(ctx, TOE_ERR_ARG, "unknown assembly variant %d", variant);
     if (variant == TOE_ASM_GATHER) TRY(mesh_build_contrib(ctx));      // one-off per mesh, outside the timed stage
     size_t n = 3 * (size_t)ctx->nq;
-    i64 nnzb = ctx->nnzb;
-    CU(ctx->val.alloc(9 * (size_t)nnzb));
+    i64 nnzb = ctx->nnzb, ldv = ctx->ldv;
+    if (ctx->val.n < 9 * (size_t)ldv + 16) {
+        CU(ctx->val.alloc(9 * (size_t)ldv + 16));
+        CU(cudaMemsetAsync(ctx->val.p, 0, ctx->val.bytes(), ctx->stream));   // plane padding is read (never used) by the SpMV's bulk copies
+    }
     TRY(reset_detj_flag(ctx));
     StageTimer T(ctx, &ctx->tm.assemble);
     // start_assemble(K, f): zero K and f (FiniteElementAnalysis.jl:211 / :661)
@@ -288,24 +291,24 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
     ctx->any_dirichlet = false;
     int ne = (int)ctx->ne;
     if (variant == TOE_ASM_ATOMIC) {
-        CU(cudaMemsetAsync(ctx->val.p, 0, 9 * (size_t)nnzb * sizeof(double), ctx->stream));
+        CU(cudaMemsetAsync(ctx->val.p, 0, (9 * (size_t)ldv + 16) * sizeof(double), ctx->stream));
         if (ctx->npc == 4)
             LAUNCH(ctx, k_asm_atomic_tet, div_up(ne, 128), 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat,
-                   (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, ctx->val.p, nnzb, ne, ctx->errflag.p);
+                   (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, ctx->val.p, ldv, ne, ctx->errflag.p);
         else
             LAUNCH(ctx, k_asm_atomic_hex, div_up((i64)ne * 8, 64), 64, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat,
-                   (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, ctx->val.p, nnzb, ne, ctx->errflag.p);
+                   (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, ctx->val.p, ldv, ne, ctx->errflag.p);
     } else {
         if (ctx->npc == 4) {
             LAUNCH(ctx, k_asm_offdiag<4>, div_up(nnzb, 128), 128, 0, (const int*)ctx->ctr_ptr.p, (const int*)ctx->ctr.p,
-                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, nnzb);
+                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, nnzb, ldv);
             LAUNCH(ctx, k_asm_diag<4>, div_up(ctx->nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->diag_slot.p,
-                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, nnzb, ctx->nq, ctx->errflag.p);
+                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p);
         } else {
             LAUNCH(ctx, k_asm_offdiag<8>, div_up(nnzb, 128), 128, 0, (const int*)ctx->ctr_ptr.p, (const int*)ctx->ctr.p,
-                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, nnzb);
+                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, nnzb, ldv);
             LAUNCH(ctx, k_asm_diag<8>, div_up(ctx->nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->diag_slot.p,
-                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, nnzb, ctx->nq, ctx->errflag.p);
+                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p);
         }
     }
     TRY(T.finish());
@@ -498,7 +501,7 @@ int compute_diag(toe_ctx* ctx) {
     TRY(ensure_vectors(ctx));
     size_t n = 3 * (size_t)ctx->nq;
     if (ctx->have_K) {
-        LAUNCH(ctx, k_diag_from_K, div_up(ctx->nq, 256), 256, 0, (const double*)ctx->val.p, ctx->nnzb, (const int*)ctx->diag_slot.p, ctx->diag.p, ctx->nq);
+        LAUNCH(ctx, k_diag_from_K, div_up(ctx->nq, 256), 256, 0, (const double*)ctx->val.p, ctx->ldv, (const int*)ctx->diag_slot.p, ctx->diag.p, ctx->nq);
     } else {
         if (ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "no operator: assemble K or set a material first");
         if (!ctx->have_pattern) return toe_fail(ctx, TOE_ERR_STATE, "no incidence lists: call toe_build_pattern first");
@@ -584,7 +587,7 @@ int apply_dirichlet(toe_ctx* ctx, const int64_t* dofs, i64 nd, double* mean_out)
         if (e) return toe_fail(ctx, TOE_ERR_ARG, "apply!: prescribed dof outside 1..%lld", (long long)n);
         if (ctx->have_K)
             LAUNCH(ctx, k_dirichlet_K, div_up(ctx->nq, 16), 128, 0, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p,
-                   (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, ctx->val.p, ctx->nnzb, ctx->nq);
+                   (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, ctx->val.p, ctx->ldv, ctx->nq);
         ctx->any_dirichlet = true;
         ctx->op_generation++;
     }
@@ -675,7 +678,7 @@ int get_values(toe_ctx* ctx, double* nzval_host) {
     if (!ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "K not assembled");
     size_t nnz = 9 * (size_t)ctx->nnzb;
     DevBuf<double> d; CU(d.alloc(nnz));
-    LAUNCH(ctx, k_scalar_values, div_up(ctx->nq, 16), 128, 0, (const int*)ctx->blk_ptr.p, (const double*)ctx->val.p, ctx->nnzb, d.p, ctx->nq);
+    LAUNCH(ctx, k_scalar_values, div_up(ctx->nq, 16), 128, 0, (const int*)ctx->blk_ptr.p, (const double*)ctx->val.p, ctx->ldv, d.p, ctx->nq);
     CU(cudaMemcpyAsync(nzval_host, d.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return TOE_OK;

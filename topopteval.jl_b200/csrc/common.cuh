@@ -98,6 +98,8 @@ struct toe_ctx {
     // block pattern (dof-node adjacency, sorted)
     DevBuf<int> blk_ptr, blk_col, diag_slot;
     i64 nnzb = 0;
+    int max_deg = 0;          // largest number of blocks in a row
+    i64 ldv = 0;              // stride between the 9 value planes (>= nnzb, multiple of 16)
     // block -> contributing (e,a,b) lists, off-diagonal blocks only (entries e*64 + a*8 + b, ascending e)
     DevBuf<int> ctr_ptr, ctr;
     // K values: 9 planes of nnzb doubles, plane k = 3*c+d holds K[3q+c, 3q'+d] of block slot s at val[k*nnzb+s]

@@ -205,7 +205,7 @@ __global__ void k_sort_inc(const int* __restrict__ inc_ptr, int* __restrict__ in
 template <int NPC, bool FILL>
 __global__ void k_adjacency(const int* __restrict__ inc_ptr, const int* __restrict__ inc, const int* __restrict__ cq,
                             int* __restrict__ deg, const int* __restrict__ blk_ptr, int* __restrict__ blk_col,
-                            int* __restrict__ diag_slot, int nq) {
+                            int* __restrict__ diag_slot, int nq, int* max_deg) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     int lo = inc_ptr[q], hi = inc_ptr[q + 1];
@@ -223,7 +223,7 @@ __global__ void k_adjacency(const int* __restrict__ inc_ptr, const int* __restri
         if (FILL) { blk_col[base + count] = next; if (next == q) diag_slot[q] = base + count; }
         prev = next; count++;
     }
-    if (!FILL) deg[q] = count;
+    if (!FILL) { deg[q] = count; atomicMax(max_deg, count); }
 }
 
 int mesh_build_pattern(toe_ctx* ctx) {
@@ -245,23 +245,27 @@ int mesh_build_pattern(toe_ctx* ctx) {
     }
     CU(ctx->blk_ptr.alloc(nq + 1));
     CU(ctx->diag_slot.alloc(nq));
+    CU(cudaMemsetAsync(ctx->errflag.p + 3, 0, sizeof(int), ctx->stream));
     if (ctx->npc == 4)
         LAUNCH(ctx, (k_adjacency<4, false>), div_up(nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p,
-               ctx->blk_ptr.p, (const int*)nullptr, (int*)nullptr, (int*)nullptr, nq);
+               ctx->blk_ptr.p, (const int*)nullptr, (int*)nullptr, (int*)nullptr, nq, ctx->errflag.p + 3);
     else
         LAUNCH(ctx, (k_adjacency<8, false>), div_up(nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p,
-               ctx->blk_ptr.p, (const int*)nullptr, (int*)nullptr, (int*)nullptr, nq);
+               ctx->blk_ptr.p, (const int*)nullptr, (int*)nullptr, (int*)nullptr, nq, ctx->errflag.p + 3);
+    CU(cudaMemcpyAsync(&ctx->max_deg, ctx->errflag.p + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     i64 nnzb = 0;
     TRY(scan_exclusive_i32(ctx, ctx->blk_ptr.p, ctx->blk_ptr.p, nq, &nnzb));
     if (nnzb * 9 > 2147483647LL * 4) return toe_fail(ctx, TOE_ERR_MESH, "pattern too large: %lld blocks", (long long)nnzb);
     ctx->nnzb = nnzb;
-    CU(ctx->blk_col.alloc(nnzb));
+    ctx->ldv = (nnzb + 15) / 16 * 16;       // plane stride: keeps every plane 128-byte aligned for the bulk copies of the SpMV
+    CU(ctx->blk_col.alloc(nnzb + 16));
+    CU(cudaMemsetAsync(ctx->blk_col.p + nnzb, 0, 16 * sizeof(int), ctx->stream));
     if (ctx->npc == 4)
         LAUNCH(ctx, (k_adjacency<4, true>), div_up(nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p,
-               (int*)nullptr, (const int*)ctx->blk_ptr.p, ctx->blk_col.p, ctx->diag_slot.p, nq);
+               (int*)nullptr, (const int*)ctx->blk_ptr.p, ctx->blk_col.p, ctx->diag_slot.p, nq, (int*)nullptr);
     else
         LAUNCH(ctx, (k_adjacency<8, true>), div_up(nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p,
-               (int*)nullptr, (const int*)ctx->blk_ptr.p, ctx->blk_col.p, ctx->diag_slot.p, nq);
+               (int*)nullptr, (const int*)ctx->blk_ptr.p, ctx->blk_col.p, ctx->diag_slot.p, nq, (int*)nullptr);
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->have_pattern = true;
     ctx->have_contrib = false; ctx->have_K = false;

@@ -31,54 +31,158 @@ __device__ __forceinline__ void cg_after_gamma(CGScalars* s, double gnew, double
 // memory; phase 2 lets one thread per scalar row add up its staged segment.  The optional epilogue fuses the CG
 // dot product p'Ap.
 // ---------------------------------------------------------------------------------------------------------
-static const int SPMV_THREADS = 192;
 static const int SPMV_ROWS = 64;           // node rows per CTA → 192 scalar rows, one per thread in phase 2
-static const int SPMV_TILE = 1152;         // block slots staged per pass (6 per thread)
+static const int SPMV_CAP = 960;           // block slots staged per pass (multiple of 4): 64 rows x 15 blocks of a structured tet mesh
+static const int SPMV_LDS = SPMV_CAP + 6;  // shared-memory plane stride (even → 16-byte aligned planes; staggers the banks of the 3 product planes)
+
+// ---- sm_100a async-copy plumbing (inline PTX): mbarrier + cp.async.bulk (SASS: UBLKCP / SYNCS) ------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ u64 l2_evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// bytes must be a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, u64 policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(256) : "memory"); }
+
+// Persistent, warp-specialised, 3-stage pipelined block-CSR SpMV.
+//   work item  = a chunk of `R` consecutive node rows = one contiguous slot range [s0,s1) of every value plane / blk_col
+//   producer   = warp 0, one lane: waits for a free stage, arms its `full` mbarrier with the byte count and issues
+//                10 bulk async copies (9 value planes + column indices, L2 evict-first) global → shared.  Two or three
+//                chunks (≈73 KB each) are always in flight per SM without occupying registers.
+//   consumers  = 8 warps: phase 1 — slot k of the stage: 9 values + column from shared memory, x[col] from global/L1,
+//                three row products written back over the slot's entries of planes 0..2; phase 2 — one thread per
+//                scalar row sums its segment, stores y and accumulates the CG dot product p'Ap in a register.
+// One partial per CTA (≤148) reaches the deterministic last-block reduction.
+static const int SPMV_CONS = 256;
+static const int SPMV_PTHREADS = SPMV_CONS + 32;
+static const int SPMV_STAGES = 3;
+static const int SPMV_LDC = SPMV_CAP + 8;  // column-index slots per stage: a chunk is fetched from a 4-aligned slot, so up to CAP+4 entries land
+static const size_t SPMV_STAGE_BYTES = (size_t)9 * SPMV_LDS * sizeof(double) + SPMV_LDC * sizeof(int);
+static const size_t SPMV_PSMEM = SPMV_STAGES * SPMV_STAGE_BYTES + 2 * SPMV_STAGES * sizeof(u64) + 32 * sizeof(double) + 16;
 
 template <bool CG>
-__global__ void __launch_bounds__(SPMV_THREADS) k_spmv_bsr(const int* __restrict__ blk_ptr, const int* __restrict__ blk_col,
-                                                           const double* __restrict__ val, i64 nnzb,
-                                                           const double* __restrict__ x, double* __restrict__ y, int nq,
-                                                           CGScalars* cg, double* partials, unsigned int* counter) {
-    __shared__ double prod[3][SPMV_TILE + 8];
-    __shared__ int sptr[SPMV_ROWS + 1];
-    __shared__ double red[32];
+__global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* __restrict__ blk_ptr, const int* __restrict__ blk_col,
+                                                                    const double* __restrict__ val, i64 ldv,
+                                                                    const double* __restrict__ x, double* __restrict__ y, int nq, int R,
+                                                                    CGScalars* cg, double* partials, unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u64* bars = reinterpret_cast<u64*>(smem_raw + SPMV_STAGES * SPMV_STAGE_BYTES);      // full[0..S), empty[0..S)
+    double* red = reinterpret_cast<double*>(bars + 2 * SPMV_STAGES);
     if (CG) { if (cg->done) return; }
-    const int t = threadIdx.x;
-    const int r0 = blockIdx.x * SPMV_ROWS;
-    const int nrows = min(SPMV_ROWS, nq - r0);
-    for (int i = t; i <= nrows; i += SPMV_THREADS) sptr[i] = __ldg(&blk_ptr[r0 + i]);
-    __syncthreads();
-    const int s0 = sptr[0], s1 = sptr[nrows];
-    const int lr = t / 3, c = t - 3 * lr;
-    const bool has_row = lr < nrows;
-    const int my_lo = has_row ? sptr[lr] : 0, my_hi = has_row ? sptr[lr + 1] : 0;
-    double acc = 0.0;
-    for (int base = s0; base < s1; base += SPMV_TILE) {
-        const int end = min(base + SPMV_TILE, s1);
-        for (int s = base + t; s < end; s += SPMV_THREADS) {
-            int col = __ldcs(&blk_col[s]);
-            const double* xp = x + 3 * (size_t)col;
-            double x0 = __ldg(xp), x1 = __ldg(xp + 1), x2 = __ldg(xp + 2);
-            const double* v = val + s;
-            double v0 = __ldcs(v), v1 = __ldcs(v + nnzb), v2 = __ldcs(v + 2 * nnzb);
-            double v3 = __ldcs(v + 3 * nnzb), v4 = __ldcs(v + 4 * nnzb), v5 = __ldcs(v + 5 * nnzb);
-            double v6 = __ldcs(v + 6 * nnzb), v7 = __ldcs(v + 7 * nnzb), v8 = __ldcs(v + 8 * nnzb);
-            int k = s - base;
-            prod[0][k] = v0 * x0 + v1 * x1 + v2 * x2;
-            prod[1][k] = v3 * x0 + v4 * x1 + v5 * x2;
-            prod[2][k] = v6 * x0 + v7 * x1 + v8 * x2;
-        }
-        __syncthreads();
-        int lo = max(my_lo, base), hi = min(my_hi, end);
-        for (int s = lo; s < hi; s++) acc += prod[c][s - base];
-        __syncthreads();
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < SPMV_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + SPMV_STAGES + s), 1); }
     }
-    size_t row = 3 * (size_t)r0 + t;
-    if (has_row) y[row] = acc;
+    __syncthreads();
+    const int nchunks = (nq + R - 1) / R;
+    double dot = 0.0;
+    if (tid >= SPMV_CONS) {
+        // ---------------- producer ----------------
+        if (tid == SPMV_CONS) {
+            const u64 pol = l2_evict_first_policy();
+            int i = 0;
+            for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, i++) {
+                const int st = i % SPMV_STAGES;
+                const unsigned ph = (unsigned)(i / SPMV_STAGES) & 1u;
+                mbar_wait(smem_u32(bars + SPMV_STAGES + st), ph ^ 1u);          // stage free (passes at once on the first lap)
+                const int r0 = chunk * R, r1 = min(r0 + R, nq);
+                const int s0 = __ldg(&blk_ptr[r0]), s1 = __ldg(&blk_ptr[r1]);
+                const int base = s0 & ~3;
+                const int cnt = ((s1 - base) + 3) & ~3;
+                double* sval = reinterpret_cast<double*>(smem_raw + st * SPMV_STAGE_BYTES);
+                int* scol = reinterpret_cast<int*>(sval + 9 * SPMV_LDS);
+                const unsigned full = smem_u32(bars + st);
+                if (cnt > 0) {
+                    mbar_expect_tx(full, (unsigned)cnt * (9 * 8 + 4));
+#pragma unroll
+                    for (int k = 0; k < 9; k++) bulk_g2s(smem_u32(sval + k * SPMV_LDS), val + (size_t)k * ldv + base, (unsigned)cnt * 8, full, pol);
+                    bulk_g2s(smem_u32(scol), blk_col + base, (unsigned)cnt * 4, full, pol);
+                } else {
+                    mbar_arrive(full);
+                }
+            }
+        }
+    } else {
+        // ---------------- consumers ----------------
+        const int lr = tid / 3, c = tid - 3 * lr;
+        int i = 0;
+        for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, i++) {
+            const int st = i % SPMV_STAGES;
+            const unsigned ph = (unsigned)(i / SPMV_STAGES) & 1u;
+            const int r0 = chunk * R, r1 = min(r0 + R, nq);
+            const int s0 = __ldg(&blk_ptr[r0]), s1 = __ldg(&blk_ptr[r1]);
+            const bool has_row = (lr < r1 - r0) && (tid < 3 * R);
+            int my_lo = 0, my_hi = 0;
+            double xrow = 0.0;
+            const size_t row = 3 * (size_t)r0 + tid;
+            if (has_row) {
+                my_lo = __ldg(&blk_ptr[r0 + lr]); my_hi = __ldg(&blk_ptr[r0 + lr + 1]);
+                if (CG) xrow = __ldg(&x[row]);
+            }
+            const int base = s0 & ~3;
+            double* sval = reinterpret_cast<double*>(smem_raw + st * SPMV_STAGE_BYTES);
+            const int* scol = reinterpret_cast<const int*>(sval + 9 * SPMV_LDS);
+            mbar_wait(smem_u32(bars + st), ph);                                  // bytes of this stage have landed
+            const int hi_s = s1 - base;
+            // all x gathers of this thread's (up to 4) slots are issued before any product is formed
+            const int k0 = s0 - base + tid;
+            double xs[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = k0 + j * SPMV_CONS;
+                const int col = k < hi_s ? scol[k] : 0;
+                const double* xp = x + 3 * (size_t)col;
+                xs[j][0] = __ldg(xp); xs[j][1] = __ldg(xp + 1); xs[j][2] = __ldg(xp + 2);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = k0 + j * SPMV_CONS;
+                if (k < hi_s) {
+                    const double* v = sval + k;
+                    const double p0 = v[0] * xs[j][0] + v[SPMV_LDS] * xs[j][1] + v[2 * SPMV_LDS] * xs[j][2];
+                    const double p1 = v[3 * SPMV_LDS] * xs[j][0] + v[4 * SPMV_LDS] * xs[j][1] + v[5 * SPMV_LDS] * xs[j][2];
+                    const double p2 = v[6 * SPMV_LDS] * xs[j][0] + v[7 * SPMV_LDS] * xs[j][1] + v[8 * SPMV_LDS] * xs[j][2];
+                    sval[k] = p0; sval[SPMV_LDS + k] = p1; sval[2 * SPMV_LDS + k] = p2;   // own slot only: no cross-thread hazard
+                }
+            }
+            consumer_sync();
+            if (has_row) {
+                const double* pr = sval + c * SPMV_LDS - base;
+                double acc = 0.0;
+                for (int k = my_lo; k < my_hi; k++) acc += pr[k];
+                y[row] = acc;
+                if (CG) dot += acc * xrow;
+            }
+            consumer_sync();
+            if (tid == 0) { fence_proxy_async(); mbar_arrive(smem_u32(bars + SPMV_STAGES + st)); }   // stage may be refilled
+        }
+    }
     if (CG) {
-        double d = has_row ? acc * __ldg(&x[row]) : 0.0;
-        d = block_sum(d, red);
+        double d = block_sum(dot, red);
         double tot;
         if (grid_sum_last_block(d, partials, counter, red, &tot)) cg_after_pAp(cg, tot);
     }
@@ -189,11 +293,21 @@ double op_bytes(toe_ctx* ctx, int matrix_free) {
 static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, CGScalars* cg, bool assume_masked) {
     if (!matrix_free) {
         if (!ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "assembled operator requested but K is not assembled");
-        unsigned grid = div_up(ctx->nq, SPMV_ROWS);
-        if (cg) LAUNCH(ctx, k_spmv_bsr<true>, grid, SPMV_THREADS, 0, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
-                       ctx->nnzb, x, y, ctx->nq, cg, ctx->partials.p, ctx->counters.p + 1);
-        else    LAUNCH(ctx, k_spmv_bsr<false>, grid, SPMV_THREADS, 0, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
-                       ctx->nnzb, x, y, ctx->nq, (CGScalars*)nullptr, (double*)nullptr, (unsigned int*)nullptr);
+        if (ctx->max_deg > SPMV_CAP) return toe_fail(ctx, TOE_ERR_MESH, "a node has %d neighbours; the SpMV stages at most %d blocks per row", ctx->max_deg, SPMV_CAP);
+        int R = SPMV_CAP / (ctx->max_deg > 0 ? ctx->max_deg : 1);
+        if (R > SPMV_ROWS) R = SPMV_ROWS;
+        int nchunks = (ctx->nq + R - 1) / R;
+        unsigned grid = (unsigned)(nchunks < N_SM ? nchunks : N_SM);          // persistent: one CTA per SM
+        static bool attr_set = false;
+        if (!attr_set) {
+            CU(cudaFuncSetAttribute(k_spmv_bsr_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_PSMEM));
+            CU(cudaFuncSetAttribute(k_spmv_bsr_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_PSMEM));
+            attr_set = true;
+        }
+        if (cg) LAUNCH(ctx, k_spmv_bsr_pipe<true>, grid, SPMV_PTHREADS, SPMV_PSMEM, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
+                       ctx->ldv, x, y, ctx->nq, R, cg, ctx->partials.p, ctx->counters.p + 1);
+        else    LAUNCH(ctx, k_spmv_bsr_pipe<false>, grid, SPMV_PTHREADS, SPMV_PSMEM, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
+                       ctx->ldv, x, y, ctx->nq, R, (CGScalars*)nullptr, (double*)nullptr, (unsigned int*)nullptr);
         return TOE_OK;
     }
     if (ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "matrix-free operator requested but no material is set");
