@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the strain-energy evaluation path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (libtopopt_b200.so through the C ABI)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: C restatement of the reference path (oracle/)
+
+A *step* is one pass of the hot path over the synthetic structured-tet cantilever: assemble K (SIMP-capable Tet4
+kernel, solid densities) → tip load → Ferrite-style Dirichlet → Jacobi-PCG to 1e-8 (Krylov.jl criterion) → per-element
+strain energy + compliance.  `value` = elements through the whole step per second with mesh, DOF map and sparsity
+pattern already resident in HBM; `e2e` = the same metric through the host API with HOST buffers (H2D of the mesh, DOF
+numbering + pattern build, the step, D2H of u) — i.e. what a reference user's script does between `setup_problem` and
+`solve_system`.  N=1 workload: the 10M-tet beam the metric is quoted on (fits one B200); N>1: the same 10M-tet beam
+partitioned over N GPUs (strong scaling), NCCL halo exchange + allreduce.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {"C3_1M": (120, 50, 28), "C4_10M": (260, 110, 58), "C5_60M": (480, 200, 104), "tiny": (24, 8, 4), "200k": (96, 32, 12)}
+CPU_SAMPLE = tuple(int(x) for x in os.environ.get("TOE_BENCH_CPU_SAMPLE", "60,20,8").split(","))   # 57 600 tets: ≈8 s (here) / ≈3 s (GPU box) of single-core CPU work per step
+TOL = 1e-8
+ITMAX = 100000
+METRIC = "elements assembled+solved/s (assemble -> Jacobi-PCG to 1e-8 -> strain energy; 10M-tet beam)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_problem(pkg, dims):
+    pts, cells = pkg.meshgen.cantilever(*dims)
+    fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0)
+    load = pkg.meshgen.nodes_at_plane(pts, 0, 60.0)
+    return pts, cells, fixed, load
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: C restatement of the reference path (single core — the reference has no threading)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_step(pkg, dims):
+    from oracle import c_oracle
+    pts, cells, fixed, load = make_problem(pkg, dims)
+    lam, mu = pkg.create_material_model(1.0, 0.3)
+    t0 = time.perf_counter()
+    cp = c_oracle.CProblem(pts, cells)                       # first-touch DOFs + sorted CSC pattern
+    cp.assemble(lam_mu=(lam, mu))                            # (q,i,j) loops + sorted-merge assembly
+    cp.apply_force(load, [0.0, 0.0, -1.0])
+    pres0 = (cp.node_first_dof[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1)
+    cp.apply_dirichlet(pres0)
+    u, niter, solved, _ = cp.pcg(TOL, ITMAX)
+    energy = cp.energy(u)
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "ne": cp.ne, "ndofs": cp.n, "niter": int(niter), "solved": solved, "energy": energy,
+            "stage_seconds": dict(cp.t), "assemble_elements_per_s": cp.ne / cp.t["assemble"]}
+
+
+def run_reference(args, pkg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dims = CPU_SAMPLE
+    for _ in range(args.warmup):
+        cpu_step(pkg, dims)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_step(pkg, dims)
+    dt = time.perf_counter() - t0
+    ne = last["ne"]
+    value = ne * args.steps / dt
+    sample = ("%dx%dx%d-cube cantilever = %d tets (%d DOFs), full path incl. DOF numbering + pattern, PCG to 1e-8 in %d iterations; "
+              "C restatement of the reference's loops (oracle/oracle.c), not Julia" % (dims + (ne, last["ndofs"], last["niter"])))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "bounded CPU sample of the cantilever workload: " + sample, "tolerance": TOL},
+            "cpu_baseline": {"value": value, "unit": "elements/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "stages": {"assemble_elements_per_s": last["assemble_elements_per_s"], "pcg_seconds": last["stage_seconds"]["pcg"],
+                       "pcg_iterations": last["niter"], "setup_seconds": last["stage_seconds"]["setup"]}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args, pkg):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
+    dims = WORKLOADS[args.workload]
+    pts, cells, fixed, load = make_problem(pkg, dims)
+    # step inputs live in pinned host memory
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    pts, cells = pin(pts), pin(cells)
+    lam, mu = pkg.create_material_model(1.0, 0.3)
+    F = [0.0, 0.0, -1.0]
+    mf = bool(args.matrix_free)
+
+    ctx = pkg.parallel.create_distributed_context(dist, local_rank) if world > 1 else pkg.Context(local_rank)
+
+    def setup():
+        ctx.set_mesh(pts, cells, distributed=world > 1)
+        ctx.build_dofs()
+        ctx.build_pattern()
+
+    def step():
+        if mf:
+            ctx.set_material_lame(lam, mu)
+        else:
+            ctx.assemble_lame(lam, mu)
+        ctx.add_nodal_force(load, F)
+        ctx.apply_dirichlet(pres)
+        st = ctx.solve_pcg(TOL, TOL, ITMAX, matrix_free=mf)
+        e, c, _ = ctx.energy()
+        return st, e, c
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    setup()
+    nfd = ctx.node_dofs()
+    pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
+    ne_total = cells.shape[0]
+
+    # ---- device-resident arm: W warm-up steps, then exactly K timed steps -------------------------------------
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = ctx.timings()["kernel_launches"]
+    sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    stage_acc = {"assemble": 0.0, "solve": 0.0, "spmv": 0.0, "energy": 0.0, "loads": 0.0, "dirichlet": 0.0}
+    st = e = c = None
+    for _ in range(args.steps):
+        st, e, c = step()
+        tm = ctx.timings()
+        stage_acc["assemble"] += tm["assemble"]; stage_acc["solve"] += tm["solve"]; stage_acc["energy"] += tm["energy"]
+        stage_acc["loads"] += tm["loads"]; stage_acc["dirichlet"] += tm["dirichlet"]; stage_acc["spmv"] += st["spmv_seconds"]
+    dev_s = ctx.timer_stop()
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.timings()["kernel_launches"] - launches0
+    dev_s = max_over_ranks(dev_s)
+    wall_s = max_over_ranks(wall_s)
+    value = ne_total * args.steps / dev_s
+
+    # dominant kernel (SpMV inside PCG): live CUDA-event timing of back-to-back launches on the library's stream
+    spmv_s, spmv_bytes = ctx.time_spmv(matrix_free=mf, reps=20)
+    spmv_s = max_over_ranks(spmv_s)
+    peaks, peak_src = measured_peaks()
+    sizes = ctx.local_sizes() if world > 1 else None
+
+    # ---- end-to-end arm: host buffers in, u + energies out, every step ---------------------------------------
+    def e2e_step():
+        setup()
+        st_, e_, c_ = step()
+        u = ctx.solution()
+        return st_, e_, c_, u
+
+    e2e_step()                                            # one warm-up (allocations are reused afterwards)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st2, e2, c2, u = e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    h2d = pts.nbytes + cells.nbytes + load.nbytes + pres.nbytes
+    d2h = u.nbytes + 2 * 8 + 128
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: structured-tet cantilever %dx%dx%d cubes x 6 = %d Tet4, %d DOFs, nnz %d; E=1, nu=0.3, solid densities, clamp x=0, "
+                                   "tip load -1 z; Jacobi-PCG atol=rtol=1e-8 (Krylov.jl M-norm)" % ((args.workload,) + dims + (ne_total, ctx.ndofs, ctx.nnz)),
+                       "operator": "matrix-free EbE" if mf else "assembled block-CSR", "parallelism": "dd%d" % world,
+                       "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (ctx.nnz * 8 / 1e9),
+                       "wall_ms_per_step": 1e3 * wall_s / args.steps},
+            "clocks": clocks,
+            "e2e": {"value": ne_total * args.steps / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_ebe_gather" if mf else "k_spmv_bsr_pipe", "bound": "hbm", "achieved": spmv_bytes / spmv_s / 1e9, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": spmv_bytes / spmv_s / 1e9 / peaks["hbm_gbs"], "traffic": profile_traffic(mf), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": spmv_bytes, "launch_seconds": spmv_s,
+                         "share_of_step": stage_acc["spmv"] / dev_s},
+            "stages": {"assemble_elements_per_s": ne_total * args.steps / stage_acc["assemble"] if stage_acc["assemble"] > 0 else None,
+                       "assemble_ms": 1e3 * stage_acc["assemble"] / args.steps, "pcg_seconds": stage_acc["solve"] / args.steps,
+                       "pcg_iterations": int(st["niter"]), "pcg_converged": bool(st["converged"]), "pcg_rel_res_l2": st["rel_res_l2"],
+                       "spmv_gbs": spmv_bytes / spmv_s / 1e9, "energy_ms": 1e3 * stage_acc["energy"] / args.steps,
+                       "energy": e, "compliance": c, "local_sizes": sizes},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_step(pkg, CPU_SAMPLE)
+            line["cpu_baseline"] = {"value": cb["ne"] / cb["seconds"], "unit": "elements/s", "cores": 1, "kind": "port",
+                                    "sample": "%dx%dx%d-cube cantilever = %d tets, full path in %.1f s (assemble %.0f el/s, PCG %d it); C restatement of the "
+                                              "reference's loops, single core like the reference (no threading in TopOptEval.jl); not Julia"
+                                              % (CPU_SAMPLE + (cb["ne"], cb["seconds"], cb["assemble_elements_per_s"], cb["niter"]))}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def profile_traffic(matrix_free):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/*.json), else None."""
+    p = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("ebe" if matrix_free else "bsr", {}).get("dram_bytes_per_launch")
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4_10M", choices=sorted(WORKLOADS))
+    ap.add_argument("--matrix-free", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    if args.impl == "reference":
+        return run_reference(args, pkg)
+    return run_b200(args, pkg)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,7 +4,7 @@ The directory name contains a dot, so it is imported through `__graft_entry__.lo
 `topopteval_jl_b200`).  Contents: `csrc/` (CUDA kernels + C ABI → libtopopt_b200.so), `_lib.py` (ctypes binding),
 `api.py` (mirror of the reference's Julia API), `julia/` (ccall shim), `vtu.py` / `meshgen.py` (harness I/O).
 """
-from . import _lib, meshgen, vtu  # noqa: F401
+from . import _lib, meshgen, parallel, vtu  # noqa: F401
 from ._lib import Context, TopOptError  # noqa: F401
 from .api import *  # noqa: F401,F403
 from . import api  # noqa: F401

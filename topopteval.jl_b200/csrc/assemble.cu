@@ -16,6 +16,9 @@
 // ---------------------------------------------------------------------------------------------------------
 static const int PARTIALS_CAP = 1 << 16;
 
+int dist_node_dofs(toe_ctx* ctx, const int** node_q_g);
+int dist_localize_cells(toe_ctx* ctx, const double* global_host, double* local_dev);
+
 int ensure_vectors(toe_ctx* ctx) {
     size_t n = 3 * (size_t)ctx->nq;
     bool fresh = ctx->f.n < n || !ctx->f.p;
@@ -411,6 +414,11 @@ __global__ void k_volume_force(const int* __restrict__ inc_ptr, const int* __res
     if (threadIdx.x == 0) partials[blockIdx.x] = bs;
 }
 
+__global__ void k_axpy1(const double* __restrict__ x, double* __restrict__ y, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
 __global__ void k_sum_partials(const double* __restrict__ partials, int n, double* out) {
     __shared__ double sh[32];
     double s = 0.0;
@@ -427,7 +435,8 @@ int add_volume_force(toe_ctx* ctx, const double b[3], double rho_uniform, const 
     double bb[3] = {b[0], b[1], b[2]};
     if (density_host) {
         CU(dens.alloc(ctx->ne));
-        CU(cudaMemcpyAsync(dens.p, density_host, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (ctx->dist) TRY(dist_localize_cells(ctx, density_host, dens.p));
+        else CU(cudaMemcpyAsync(dens.p, density_host, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         dptr = dens.p;
     } else {
         if (rho_uniform == 0.0) return toe_fail(ctx, TOE_ERR_ARG, "apply_volume_force!: density must be non-zero");
@@ -437,13 +446,22 @@ int add_volume_force(toe_ctx* ctx, const double b[3], double rho_uniform, const 
     StageTimer T(ctx, &ctx->tm.loads);
     unsigned grid = div_up(ctx->nq, 128);
     DevBuf<double> part; CU(part.alloc(grid + 1));
+    // partitioned: the per-rank partial load goes to a scratch vector, is summed over the interface, then added to f
+    double* target = ctx->f.p;
+    size_t n = 3 * (size_t)ctx->nq;
+    if (ctx->dist) { target = ctx->tmp.p; CU(cudaMemsetAsync(target, 0, n * sizeof(double), ctx->stream)); }
     if (ctx->npc == 4)
         LAUNCH(ctx, k_volume_force<4>, grid, 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p,
-               dptr, rho_uniform, skip_below, bb[0], bb[1], bb[2], ctx->f.p, ctx->nq, part.p);
+               dptr, rho_uniform, skip_below, bb[0], bb[1], bb[2], target, ctx->nq, part.p);
     else
         LAUNCH(ctx, k_volume_force<8>, grid, 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p,
-               dptr, rho_uniform, skip_below, bb[0], bb[1], bb[2], ctx->f.p, ctx->nq, part.p);
+               dptr, rho_uniform, skip_below, bb[0], bb[1], bb[2], target, ctx->nq, part.p);
     LAUNCH(ctx, k_sum_partials, 1, 256, 0, (const double*)part.p, (int)grid, part.p + grid);
+    if (ctx->dist) {
+        TRY(dist_post_spmv(ctx, target));
+        LAUNCH(ctx, k_axpy1, div_up((i64)n, 256), 256, 0, (const double*)target, ctx->f.p, n);
+        TRY(dist_allreduce(ctx, part.p + grid, 1));
+    }
     double mass = 0.0;
     CU(cudaMemcpyAsync(&mass, part.p + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     TRY(T.finish());
@@ -519,28 +537,36 @@ int compute_diag(toe_ctx* ctx) {
     return TOE_OK;
 }
 
-__global__ void k_abs_sum(const double* __restrict__ x, size_t n, double* __restrict__ partials, unsigned int* counter, double* out) {
+__global__ void k_abs_sum(const double* __restrict__ x, size_t n, const unsigned char* __restrict__ owned, double* __restrict__ partials,
+                          unsigned int* counter, double* out) {
     __shared__ double sh[32];
     double s = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += fabs(x[i]);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (!owned || owned[i / 3]) s += fabs(x[i]);
     s = block_sum(s, sh);
     double tot;
     if (grid_sum_last_block(s, partials, counter, sh, &tot)) *out = tot;
 }
 
-__global__ void k_mark_dirichlet(const int64_t* __restrict__ dofs, i64 nd, size_t n, const double* __restrict__ m_dev, double inv_n,
+__global__ void k_mark_dirichlet(const int64_t* __restrict__ dofs, i64 nd, size_t n, const int* __restrict__ glob2loc,
+                                 const double* __restrict__ m_dev, double inv_n,
                                  unsigned char* dflag, double* dval, double* diag, double* f, int* err) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nd) return;
     int64_t d = dofs[i];
-    if (d < 1 || (size_t)d > n) { atomicExch(err + 2, 1); return; }
+    if (d < 1 || (size_t)d > n) { atomicExch(err + 2, 1); return; }        // n = global number of DOFs
+    if (glob2loc) {                                                         // partitioned: keep only dofs of local nodes
+        int l = glob2loc[(d - 1) / 3];
+        if (l < 0) return;
+        d = 3 * (int64_t)l + (d - 1) % 3 + 1;
+    }
     double m = *m_dev * inv_n;
     dflag[d - 1] = 1; dval[d - 1] = m; diag[d - 1] = m; f[d - 1] = 0.0;
 }
 
 // 8 lanes per block row: zero the stored entries of prescribed rows / columns, put m on the diagonal
 __global__ void k_dirichlet_K(const int* __restrict__ blk_ptr, const int* __restrict__ blk_col, const unsigned char* __restrict__ dflag,
-                              const double* __restrict__ dval, double* __restrict__ val, i64 nnzb, int nq) {
+                              const double* __restrict__ dval, const unsigned char* __restrict__ owned, double* __restrict__ val, i64 nnzb, int nq) {
     int q = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
     if (q >= nq) return;
     int sub = threadIdx.x & 7;
@@ -555,7 +581,7 @@ __global__ void k_dirichlet_K(const int* __restrict__ blk_ptr, const int* __rest
             for (int d = 0; d < 3; d++)
                 if (fr[c] | fc[d]) {
                     double v = 0.0;
-                    if (col == q && c == d) v = dval[3 * (size_t)q + c];
+                    if (col == q && c == d && (!owned || owned[q])) v = dval[3 * (size_t)q + c];   // sub-assembled K: m sits on the owner's copy only
                     val[(size_t)(3 * c + d) * nnzb + s] = v;
                 }
     }
@@ -570,24 +596,25 @@ int apply_dirichlet(toe_ctx* ctx, const int64_t* dofs, i64 nd, double* mean_out)
     StageTimer T(ctx, &ctx->tm.dirichlet);
     // m = mean(abs(diag K)) of the incoming K  (Ferrite apply!, meandiag)
     double* m_dev = &ctx->cgs.p->aux;
-    LAUNCH(ctx, k_abs_sum, min_u(div_up((i64)n, 256), 1024u), 256, 0, (const double*)ctx->diag.p, n, ctx->partials.p, ctx->counters.p, m_dev);
+    LAUNCH(ctx, k_abs_sum, min_u(div_up((i64)n, 256), 1024u), 256, 0, (const double*)ctx->diag.p, n, ctx->owned, ctx->partials.p, ctx->counters.p, m_dev);
     TRY(dist_allreduce(ctx, m_dev, 1));
     double msum = 0.0;
     CU(cudaMemcpyAsync(&msum, m_dev, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    double inv_n = 1.0 / (double)n;
+    size_t nglob = ctx->n_global ? (size_t)ctx->n_global : n;
+    double inv_n = 1.0 / (double)nglob;
     if (nd > 0) {
         DevBuf<int64_t> d; CU(d.alloc(nd));
         CU(cudaMemcpyAsync(d.p, dofs, nd * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, k_mark_dirichlet, div_up(nd, 128), 128, 0, (const int64_t*)d.p, nd, n, (const double*)m_dev, inv_n,
+        LAUNCH(ctx, k_mark_dirichlet, div_up(nd, 128), 128, 0, (const int64_t*)d.p, nd, nglob, ctx->glob2loc, (const double*)m_dev, inv_n,
                ctx->dflag.p, ctx->dval.p, ctx->diag.p, ctx->f.p, ctx->errflag.p);
         int e = 0;
         CU(cudaMemcpyAsync(&e, ctx->errflag.p + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        if (e) return toe_fail(ctx, TOE_ERR_ARG, "apply!: prescribed dof outside 1..%lld", (long long)n);
+        if (e) return toe_fail(ctx, TOE_ERR_ARG, "apply!: prescribed dof outside 1..%lld", (long long)nglob);
         if (ctx->have_K)
             LAUNCH(ctx, k_dirichlet_K, div_up(ctx->nq, 16), 128, 0, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p,
-                   (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, ctx->val.p, ctx->ldv, ctx->nq);
+                   (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, ctx->owned, ctx->val.p, ctx->ldv, ctx->nq);
         ctx->any_dirichlet = true;
         ctx->op_generation++;
     }
@@ -645,7 +672,9 @@ __global__ void k_scalar_values(const int* __restrict__ blk_ptr, const double* _
 int get_node_dofs(toe_ctx* ctx, int64_t* out_host) {
     if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "DOFs not built");
     DevBuf<int64_t> d; CU(d.alloc(ctx->nn));
-    LAUNCH(ctx, k_node_first_dof, div_up(ctx->nn, 256), 256, 0, (const int*)ctx->node_q.p, d.p, ctx->nn);
+    const int* nq_map = ctx->node_q.p;
+    if (ctx->dist) TRY(dist_node_dofs(ctx, &nq_map));          // partitioned: ctx->node_q is the local map, the ABI wants the global one
+    LAUNCH(ctx, k_node_first_dof, div_up(ctx->nn, 256), 256, 0, nq_map, d.p, ctx->nn);
     CU(cudaMemcpyAsync(out_host, d.p, ctx->nn * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return TOE_OK;

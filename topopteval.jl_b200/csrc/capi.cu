@@ -28,6 +28,10 @@ int dist_gather_solution(toe_ctx* ctx, double* u_host);
 int dist_scatter_vector(toe_ctx* ctx, const double* global_host, double* local_dev);
 int dist_gather_vector(toe_ctx* ctx, const double* local_dev, double* global_host);
 bool dist_active(toe_ctx* ctx);
+int dist_localize_cells(toe_ctx* ctx, const double* global_host, double* local_dev);
+int dist_node_dofs(toe_ctx* ctx, const int** node_q_g);
+i64 dist_global_ne(toe_ctx* ctx);
+i64 dist_global_ndofs(toe_ctx* ctx);
 
 static std::string g_create_error;
 static std::mutex g_mutex;
@@ -130,12 +134,16 @@ int toe_build_dofs(toe_ctx* ctx, int64_t* ndofs_out) {
     StageTimer T(ctx, &ctx->tm.build_dofs);
     if (!ctx->have_dofs) TRY(mesh_build_dofs(ctx));
     TRY(T.finish());
-    if (ndofs_out) *ndofs_out = 3 * (int64_t)ctx->nq;
+    if (ndofs_out) *ndofs_out = dist_global_ndofs(ctx);      // partitioned: the global count (u crosses the ABI in global Ferrite order)
     return TOE_OK;
 }
 
 int toe_get_node_dofs(toe_ctx* ctx, int64_t* node_first_dof) { GUARD(ctx); if (!node_first_dof) return TOE_ERR_ARG; return get_node_dofs(ctx, node_first_dof); }
-int toe_get_cell_dofs(toe_ctx* ctx, int64_t first, int64_t count, int64_t* out) { GUARD(ctx); if (!out) return TOE_ERR_ARG; return get_cell_dofs(ctx, first, count, out); }
+int toe_get_cell_dofs(toe_ctx* ctx, int64_t first, int64_t count, int64_t* out) {
+    GUARD(ctx); if (!out) return TOE_ERR_ARG;
+    if (dist_active(ctx)) return toe_fail(ctx, TOE_ERR_STATE, "toe_get_cell_dofs: not available on a partitioned ctx (cells are distributed)");
+    return get_cell_dofs(ctx, first, count, out);
+}
 
 int toe_build_pattern(toe_ctx* ctx, int64_t* nnz_out) {
     GUARD(ctx);
@@ -147,7 +155,11 @@ int toe_build_pattern(toe_ctx* ctx, int64_t* nnz_out) {
     return TOE_OK;
 }
 
-int toe_get_pattern(toe_ctx* ctx, int64_t* colptr, int64_t* rowval) { GUARD(ctx); if (!colptr || !rowval) return TOE_ERR_ARG; return get_pattern(ctx, colptr, rowval); }
+int toe_get_pattern(toe_ctx* ctx, int64_t* colptr, int64_t* rowval) {
+    GUARD(ctx); if (!colptr || !rowval) return TOE_ERR_ARG;
+    if (dist_active(ctx)) return toe_fail(ctx, TOE_ERR_STATE, "toe_get_pattern: K is sub-assembled per partition; not available on a partitioned ctx");
+    return get_pattern(ctx, colptr, rowval);
+}
 
 static int set_material_common(toe_ctx* ctx) {
     if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "material: call setup_problem (toe_build_dofs) first");
@@ -167,7 +179,8 @@ static int set_simp(toe_ctx* ctx, double E0, double nu, double Emin, double p, c
     TRY(set_material_common(ctx));
     if (!density) return toe_fail(ctx, TOE_ERR_ARG, "SIMP material needs a density vector");
     CU(ctx->density.alloc(ctx->ne));
-    CU(cudaMemcpyAsync(ctx->density.p, density, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (dist_active(ctx)) TRY(dist_localize_cells(ctx, density, ctx->density.p));     // density_data is indexed by global cell id
+    else CU(cudaMemcpyAsync(ctx->density.p, density, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->mat = Material();
     ctx->mat.mode = MAT_SIMP; ctx->mat.E0 = E0; ctx->mat.nu = nu; ctx->mat.Emin = Emin; ctx->mat.p = p;
     ctx->mat.density = ctx->density.p;
@@ -178,8 +191,11 @@ static int set_percell(toe_ctx* ctx, const double* lam, const double* mu) {
     TRY(set_material_common(ctx));
     if (!lam || !mu) return toe_fail(ctx, TOE_ERR_ARG, "per-cell material needs lambda and mu vectors");
     CU(ctx->lam_e.alloc(ctx->ne)); CU(ctx->mu_e.alloc(ctx->ne));
-    CU(cudaMemcpyAsync(ctx->lam_e.p, lam, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->mu_e.p, mu, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (dist_active(ctx)) { TRY(dist_localize_cells(ctx, lam, ctx->lam_e.p)); TRY(dist_localize_cells(ctx, mu, ctx->mu_e.p)); }
+    else {
+        CU(cudaMemcpyAsync(ctx->lam_e.p, lam, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->mu_e.p, mu, ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->mat = Material();
     ctx->mat.mode = MAT_PERCELL; ctx->mat.lam_e = ctx->lam_e.p; ctx->mat.mu_e = ctx->mu_e.p;
     return TOE_OK;
@@ -212,8 +228,16 @@ int toe_set_material_simp(toe_ctx* ctx, double E0, double nu, double Emin, doubl
     GUARD(ctx); TRY(set_simp(ctx, E0, nu, Emin, p, density)); return reset_for_matrix_free(ctx);
 }
 
-int toe_ke_batch(toe_ctx* ctx, int64_t first, int64_t count, double* ke_out) { GUARD(ctx); if (!ke_out) return TOE_ERR_ARG; return ke_batch(ctx, first, count, ke_out); }
-int toe_get_values(toe_ctx* ctx, double* nzval) { GUARD(ctx); if (!nzval) return TOE_ERR_ARG; return get_values(ctx, nzval); }
+int toe_ke_batch(toe_ctx* ctx, int64_t first, int64_t count, double* ke_out) {
+    GUARD(ctx); if (!ke_out) return TOE_ERR_ARG;
+    if (dist_active(ctx)) return toe_fail(ctx, TOE_ERR_STATE, "toe_ke_batch: not available on a partitioned ctx");
+    return ke_batch(ctx, first, count, ke_out);
+}
+int toe_get_values(toe_ctx* ctx, double* nzval) {
+    GUARD(ctx); if (!nzval) return TOE_ERR_ARG;
+    if (dist_active(ctx)) return toe_fail(ctx, TOE_ERR_STATE, "toe_get_values: K is sub-assembled per partition; not available on a partitioned ctx");
+    return get_values(ctx, nzval);
+}
 
 static int get_vec(toe_ctx* ctx, const double* dev, double* host) {
     if (!host) return TOE_ERR_ARG;

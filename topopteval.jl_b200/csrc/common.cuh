@@ -130,6 +130,10 @@ struct toe_ctx {
     CGScalars* cgs_host = nullptr;   // pinned readback buffer
 
     DistState* dist = nullptr;
+    // views set by the multi-GPU layer (null / 0 on a single GPU)
+    const unsigned char* owned = nullptr;   // per local dof-node: 1 if this rank owns it (masked reductions, Dirichlet diagonal)
+    const int* glob2loc = nullptr;          // global dof-node id -> local id, -1 if not on this rank
+    i64 n_global = 0;                       // global number of DOFs (0 = same as local)
 };
 
 inline int toe_fail(toe_ctx* c, int code, const char* fmt, ...) {
@@ -229,4 +233,5 @@ int op_apply(toe_ctx* ctx, const double* x, double* y, int matrix_free, double* 
 double op_bytes(toe_ctx* ctx, int matrix_free);
 int dist_post_spmv(toe_ctx* ctx, double* y);      // interface sum (no-op without dist)
 int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count);
+int dist_sum_per_element(toe_ctx* ctx, const double* local_dev, double* global_host);   // per-cell output, global cell order
 void dist_destroy(toe_ctx* ctx);

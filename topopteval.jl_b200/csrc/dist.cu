@@ -1,19 +1,510 @@
-// dist.cu — multi-GPU layer (one ctx per GPU / process).  Placeholder: the single-GPU hooks are no-ops.
+// dist.cu — multi-GPU layer: one ctx per GPU / process, element-based domain decomposition.
+//
+// The reference is single-process, single-threaded; this layer is new.  Every rank receives the same
+// global mesh, numbers the DOFs globally (so `u` comes back in the reference's Ferrite order), splits the cells by
+// recursive coordinate bisection of their centroids — computed redundantly and deterministically on every GPU, so
+// no partition data is exchanged — and keeps its own cells plus the nodes they touch.  K is sub-assembled per part
+// (assembly needs no communication); vectors are stored "interface-consistent" (every rank holding a node holds its
+// full value).  One operator application = local product + interface sum: pack → ncclSend/ncclRecv with every
+// neighbouring part → unpack, contributions added in ascending rank order so that all copies of an interface value
+// are bit-identical.  Dot products are owner-masked and closed by ncclAllReduce.  NCCL is dlopen'ed (libnccl.so.2).
 #include "common.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
+#include <algorithm>
+#include <cstring>
 
-struct DistState { int nranks = 1, rank = 0; };
+struct NcclApi {
+    void* h = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load(std::string& err) {
+    if (g_nccl.h) return TOE_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return TOE_ERR_COMM; }
+#define SYM(f) g_nccl.f = (decltype(g_nccl.f))dlsym(h, "nccl" #f); if (!g_nccl.f) { err = "libnccl lacks nccl" #f; return TOE_ERR_COMM; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllReduce) SYM(Send) SYM(Recv) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+    g_nccl.h = h;
+    return TOE_OK;
+}
+
+#define NC(call) do { ncclResult_t _r = (call); if (_r != ncclSuccess) \
+    return toe_fail(ctx, TOE_ERR_COMM, "NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(_r)); } while (0)
+
+struct DistState {
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    // global problem
+    i64 nn_g = 0, ne_g = 0;
+    int nq_g = 0;
+    DevBuf<int> node_q_g;        // nn_g: global dof-node id of each mesh node (or -1)
+    DevBuf<int> part;            // ne_g: part id of every global cell
+    DevBuf<int> eloc2glob;       // ne_local: global cell id of each local cell (ascending)
+    DevBuf<int> loc2glob;        // nq_local: global dof-node id of each local dof-node (ascending)
+    DevBuf<int> glob2loc;        // nq_g
+    DevBuf<unsigned char> owned; // nq_local
+    // interface exchange
+    std::vector<int> nbr;                 // neighbouring ranks (ascending)
+    std::vector<int> nbr_count;           // shared nodes with each neighbour
+    std::vector<int> nbr_off;             // offset (in nodes) of each neighbour's segment in the send/recv buffers
+    int n_shared_total = 0;               // Σ nbr_count
+    int n_if = 0;                         // local interface nodes
+    DevBuf<int> send_nodes;               // n_shared_total: local node id per send slot
+    DevBuf<double> sendbuf, recvbuf;      // 3 * n_shared_total
+    DevBuf<int> if_node, if_ptr, if_src;  // unpack CSR: for interface node i, sources in ascending rank order; src = -1 → own value, else recv slot
+    DevBuf<double> gvec;                  // global-length scratch for gathers
+};
 
 bool dist_active(toe_ctx* ctx) { return ctx->dist != nullptr; }
-void dist_destroy(toe_ctx* ctx) { delete ctx->dist; ctx->dist = nullptr; }
-int dist_post_spmv(toe_ctx* ctx, double*) { (void)ctx; return TOE_OK; }
-int dist_allreduce(toe_ctx* ctx, double*, int) { (void)ctx; return TOE_OK; }
-int dist_comm_unique_id(char id_out[128], std::string& err) { (void)id_out; err = "multi-GPU layer not built"; return TOE_ERR_COMM; }
-int dist_comm_init(toe_ctx* ctx, int, int, const char*) { return toe_fail(ctx, TOE_ERR_COMM, "multi-GPU layer not built"); }
-int dist_set_mesh(toe_ctx* ctx, i64, const double*, i64, int, const int64_t*) { return toe_fail(ctx, TOE_ERR_COMM, "multi-GPU layer not built"); }
-int dist_get_partition(toe_ctx* ctx, int32_t*) { return toe_fail(ctx, TOE_ERR_COMM, "multi-GPU layer not built"); }
-int dist_local_sizes(toe_ctx* ctx, int64_t* a, int64_t* b, int64_t* c, int64_t* d) {
-    if (a) *a = ctx->ne; if (b) *b = 3 * (int64_t)ctx->nq; if (c) *c = 9 * ctx->nnzb; if (d) *d = 0; return TOE_OK;
+
+void dist_destroy(toe_ctx* ctx) {
+    if (!ctx->dist) return;
+    if (ctx->dist->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->dist->comm);
+    delete ctx->dist;
+    ctx->dist = nullptr; ctx->owned = nullptr; ctx->glob2loc = nullptr; ctx->n_global = 0;
 }
-int dist_gather_vector(toe_ctx* ctx, const double*, double*) { return toe_fail(ctx, TOE_ERR_COMM, "multi-GPU layer not built"); }
-int dist_scatter_vector(toe_ctx* ctx, const double*, double*) { return toe_fail(ctx, TOE_ERR_COMM, "multi-GPU layer not built"); }
-int solve_pcg_dist(toe_ctx* ctx, double, double, i64, int, toe_pcg_stats*, double*, i64) { return toe_fail(ctx, TOE_ERR_COMM, "multi-GPU layer not built"); }
+
+int dist_comm_unique_id(char id_out[128], std::string& err) {
+    TRY(nccl_load(err));
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { err = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return TOE_ERR_COMM; }
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id_out, &id, 128);
+    return TOE_OK;
+}
+
+int dist_comm_init(toe_ctx* ctx, int nranks, int rank, const char id[128]) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return toe_fail(ctx, TOE_ERR_ARG, "toe_comm_init: bad rank %d of %d", rank, nranks);
+    if (nranks & (nranks - 1)) return toe_fail(ctx, TOE_ERR_ARG, "toe_comm_init: the bisection partitioner needs a power-of-two number of ranks, got %d", nranks);
+    if (nranks > 32) return toe_fail(ctx, TOE_ERR_ARG, "toe_comm_init: at most 32 ranks");
+    std::string err;
+    if (nccl_load(err) != TOE_OK) return toe_fail(ctx, TOE_ERR_COMM, "%s", err.c_str());
+    dist_destroy(ctx);
+    DistState* d = new DistState();
+    d->nranks = nranks; d->rank = rank;
+    ncclUniqueId uid; memcpy(&uid, id, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&d->comm, nranks, uid, rank);
+    if (r != ncclSuccess) { delete d; return toe_fail(ctx, TOE_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    ctx->dist = d;
+    return TOE_OK;
+}
+
+int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count) {
+    if (!ctx->dist || ctx->dist->nranks == 1) return TOE_OK;
+    NC(g_nccl.AllReduce(dev_vals, dev_vals, (size_t)count, ncclDouble, ncclSum, ctx->dist->comm, ctx->stream));
+    return TOE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// recursive coordinate bisection by exact radix selection on (quantised centroid coordinate, cell id) keys
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 enc_double(double x) {      // order-preserving map double -> u64
+    u64 b = (u64)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__host__ __device__ inline double dec_double(u64 k) {
+    u64 b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    double x; memcpy(&x, &b, 8); return x;
+}
+
+__global__ void k_bbox(const double* __restrict__ xyz, i64 nn, u64* mn, u64* mx) {
+    i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 lo[3] = {~0ULL, ~0ULL, ~0ULL}, hi[3] = {0, 0, 0};
+    if (g < nn) for (int c = 0; c < 3; c++) { u64 k = enc_double(xyz[3 * g + c]); lo[c] = k; hi[c] = k; }
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o > 0; o >>= 1) {
+            u64 a = __shfl_xor_sync(0xffffffffu, lo[c], o), b = __shfl_xor_sync(0xffffffffu, hi[c], o);
+            lo[c] = a < lo[c] ? a : lo[c]; hi[c] = b > hi[c] ? b : hi[c];
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&mn[c], lo[c]); atomicMax(&mx[c], hi[c]); }
+    }
+}
+
+struct SplitParams {          // per current part (max 16 parts before the last split of 32)
+    int axis[16];
+    double lo[16], scale[16];
+    u64 prefix[16];           // key prefix selected so far
+    u64 thresh[16];
+};
+
+__device__ __forceinline__ u64 cell_key(const int* __restrict__ conn0, const double* __restrict__ xyz, int npc, i64 e, int axis, double lo, double scale) {
+    double s = 0.0;
+    for (int a = 0; a < npc; a++) s += xyz[3 * (size_t)conn0[e * npc + a] + axis];
+    s /= (double)npc;
+    double q = (s - lo) * scale;
+    if (q < 0) q = 0; if (q > 4294967295.0) q = 4294967295.0;
+    return ((u64)(unsigned int)q << 32) | (u64)(unsigned int)e;
+}
+
+// histogram of the 16-bit digit `pass` (0 = most significant) among cells whose higher digits equal prefix[part]
+__global__ void k_split_hist(const int* __restrict__ conn0, const double* __restrict__ xyz, int npc, i64 ne, const int* __restrict__ part,
+                             SplitParams sp, int pass, unsigned int* __restrict__ hist) {
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int p = part[e];
+    u64 key = cell_key(conn0, xyz, npc, e, sp.axis[p], sp.lo[p], sp.scale[p]);
+    int shift = 16 * (3 - pass);
+    if (pass > 0 && (key >> (shift + 16)) != sp.prefix[p]) return;
+    unsigned int digit = (unsigned int)(key >> shift) & 0xffffu;
+    atomicAdd(&hist[(size_t)p * 65536 + digit], 1u);
+}
+
+__global__ void k_split_apply(const int* __restrict__ conn0, const double* __restrict__ xyz, int npc, i64 ne, int* __restrict__ part, SplitParams sp) {
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int p = part[e];
+    u64 key = cell_key(conn0, xyz, npc, e, sp.axis[p], sp.lo[p], sp.scale[p]);
+    part[e] = 2 * p + (key >= sp.thresh[p] ? 1 : 0);
+}
+
+static int partition_rcb(toe_ctx* ctx, DistState* d) {
+    i64 ne = d->ne_g;
+    int npc = ctx->npc;
+    CU(d->part.alloc(ne));
+    CU(cudaMemsetAsync(d->part.p, 0, ne * sizeof(int), ctx->stream));
+    if (d->nranks == 1) return TOE_OK;
+    DevBuf<u64> bb; CU(bb.alloc(6));
+    u64 init[6] = {~0ULL, ~0ULL, ~0ULL, 0, 0, 0};
+    CU(cudaMemcpyAsync(bb.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_bbox, div_up(d->nn_g, 256), 256, 0, (const double*)ctx->xyz.p, d->nn_g, bb.p, bb.p + 3);
+    u64 hb[6];
+    CU(cudaMemcpyAsync(hb, bb.p, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    double glo[3], ghi[3];
+    for (int c = 0; c < 3; c++) { glo[c] = dec_double(hb[c]); ghi[c] = dec_double(hb[3 + c]); }
+    std::vector<double> ext(3 * 32);
+    std::vector<i64> count(32, 0);
+    for (int c = 0; c < 3; c++) ext[c] = ghi[c] - glo[c];
+    count[0] = ne;
+    DevBuf<unsigned int> hist; CU(hist.alloc((size_t)16 * 65536));
+    std::vector<unsigned int> hh((size_t)16 * 65536);
+    for (int nparts = 1; nparts < d->nranks; nparts *= 2) {
+        SplitParams sp;
+        memset(&sp, 0, sizeof sp);
+        std::vector<i64> target(nparts), rem(nparts);
+        for (int p = 0; p < nparts; p++) {
+            int ax = 0;
+            for (int c = 1; c < 3; c++) if (ext[3 * p + c] > ext[3 * p + ax]) ax = c;
+            sp.axis[p] = ax; sp.lo[p] = glo[ax];
+            sp.scale[p] = (ghi[ax] > glo[ax]) ? 4294967295.0 / (ghi[ax] - glo[ax]) : 0.0;
+            target[p] = count[p] / 2;            // cells that go to the lower child
+            rem[p] = target[p];
+        }
+        for (int pass = 0; pass < 4; pass++) {
+            CU(cudaMemsetAsync(hist.p, 0, (size_t)nparts * 65536 * sizeof(unsigned int), ctx->stream));
+            LAUNCH(ctx, k_split_hist, div_up(ne, 256), 256, 0, (const int*)ctx->conn0.p, (const double*)ctx->xyz.p, npc, ne, (const int*)d->part.p, sp, pass, hist.p);
+            CU(cudaMemcpyAsync(hh.data(), hist.p, (size_t)nparts * 65536 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (int p = 0; p < nparts; p++) {
+                const unsigned int* h = hh.data() + (size_t)p * 65536;
+                i64 cum = 0; int dg = 0;
+                for (; dg < 65535; dg++) { if (cum + h[dg] > rem[p]) break; cum += h[dg]; }
+                rem[p] -= cum;
+                sp.prefix[p] = (sp.prefix[p] << 16) | (u64)dg;
+            }
+        }
+        for (int p = 0; p < nparts; p++) sp.thresh[p] = sp.prefix[p];     // key of the cell with rank target[p]
+        LAUNCH(ctx, k_split_apply, div_up(ne, 256), 256, 0, (const int*)ctx->conn0.p, (const double*)ctx->xyz.p, npc, ne, d->part.p, sp);
+        std::vector<double> next(3 * 32);
+        std::vector<i64> ncount(32, 0);
+        for (int p = nparts - 1; p >= 0; p--) {
+            for (int c = 0; c < 3; c++) { double v = ext[3 * p + c] * (c == sp.axis[p] ? 0.5 : 1.0); next[3 * (2 * p) + c] = v; next[3 * (2 * p + 1) + c] = v; }
+            ncount[2 * p] = target[p]; ncount[2 * p + 1] = count[p] - target[p];
+        }
+        ext = next; count = ncount;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TOE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// local sub-mesh extraction
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_flag_eq(const int* __restrict__ a, int v, int* __restrict__ flag, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = a[i] == v ? 1 : 0;
+}
+__global__ void k_compact_cells(const int* __restrict__ part, int rank, const int* __restrict__ pos, const int* __restrict__ cq_g, int npc,
+                                int* __restrict__ eloc2glob, int* __restrict__ cq_tmp, int* __restrict__ touched, i64 ne) {
+    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne || part[e] != rank) return;
+    int j = pos[e];
+    eloc2glob[j] = (int)e;
+    for (int a = 0; a < npc; a++) { int q = cq_g[e * npc + a]; cq_tmp[(size_t)j * npc + a] = q; touched[q] = 1; }
+}
+__global__ void k_rank_mask(const int* __restrict__ part, const int* __restrict__ cq_g, int npc, unsigned int* __restrict__ mask, i64 ne) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ne * npc) return;
+    atomicOr(&mask[cq_g[i]], 1u << part[i / npc]);
+}
+__global__ void k_glob2loc(const int* __restrict__ touched, const int* __restrict__ pos, int* __restrict__ glob2loc, int* __restrict__ loc2glob,
+                           const double* __restrict__ xq_g, double* __restrict__ xq_l, const unsigned int* __restrict__ mask, int rank,
+                           unsigned char* __restrict__ owned, unsigned int* __restrict__ mask_l, int nq_g) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq_g) return;
+    if (!touched[q]) { glob2loc[q] = -1; return; }
+    int l = pos[q];
+    glob2loc[q] = l; loc2glob[l] = q;
+    xq_l[3 * (size_t)l] = xq_g[3 * (size_t)q]; xq_l[3 * (size_t)l + 1] = xq_g[3 * (size_t)q + 1]; xq_l[3 * (size_t)l + 2] = xq_g[3 * (size_t)q + 2];
+    unsigned int m = mask[q];
+    mask_l[l] = m;
+    owned[l] = ((m & (0u - m)) == (1u << rank)) ? 1 : 0;      // lowest touching rank owns the node
+}
+__global__ void k_remap(const int* __restrict__ in, const int* __restrict__ map, int* __restrict__ out, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] >= 0 ? map[in[i]] : -1;
+}
+
+int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, const int64_t* conn) {
+    DistState* d = ctx->dist;
+    if (!d) return toe_fail(ctx, TOE_ERR_STATE, "toe_set_mesh_distributed: call toe_comm_init first");
+    ctx->owned = nullptr; ctx->glob2loc = nullptr; ctx->n_global = 0;
+    TRY(mesh_upload(ctx, nn, xyz, ne, npc, conn));
+    TRY(mesh_build_dofs(ctx));                 // global first-touch numbering: identical to the 1-GPU numbering
+    d->nn_g = nn; d->ne_g = ne; d->nq_g = ctx->nq;
+    TRY(partition_rcb(ctx, d));
+    // local cells (ascending global id)
+    DevBuf<int> flag; CU(flag.alloc(std::max<i64>(ne, d->nq_g) + 1));
+    LAUNCH(ctx, k_flag_eq, div_up(ne, 256), 256, 0, (const int*)d->part.p, d->rank, flag.p, ne);
+    i64 ne_l = 0;
+    TRY(scan_exclusive_i32(ctx, flag.p, flag.p, ne, &ne_l));
+    if (ne_l == 0) return toe_fail(ctx, TOE_ERR_MESH, "rank %d received no cells", d->rank);
+    CU(d->eloc2glob.alloc(ne_l));
+    DevBuf<int> cq_tmp, touched; CU(cq_tmp.alloc(ne_l * npc)); CU(touched.alloc(d->nq_g + 1));
+    CU(cudaMemsetAsync(touched.p, 0, (d->nq_g + 1) * sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_compact_cells, div_up(ne, 256), 256, 0, (const int*)d->part.p, d->rank, (const int*)flag.p, (const int*)ctx->cq.p, npc,
+           d->eloc2glob.p, cq_tmp.p, touched.p, ne);
+    // rank masks of every global dof-node
+    DevBuf<unsigned int> mask; CU(mask.alloc(d->nq_g));
+    CU(cudaMemsetAsync(mask.p, 0, d->nq_g * sizeof(unsigned int), ctx->stream));
+    LAUNCH(ctx, k_rank_mask, div_up(ne * npc, 256), 256, 0, (const int*)d->part.p, (const int*)ctx->cq.p, npc, mask.p, ne);
+    // local dof-nodes (ascending global id)
+    DevBuf<int> pos; CU(pos.alloc(d->nq_g + 1));
+    i64 nq_l = 0;
+    TRY(scan_exclusive_i32(ctx, touched.p, pos.p, d->nq_g, &nq_l));
+    CU(d->glob2loc.alloc(d->nq_g)); CU(d->loc2glob.alloc(nq_l)); CU(d->owned.alloc(nq_l));
+    DevBuf<double> xq_l; CU(xq_l.alloc(3 * nq_l));
+    DevBuf<unsigned int> mask_l; CU(mask_l.alloc(nq_l));
+    LAUNCH(ctx, k_glob2loc, div_up(d->nq_g, 256), 256, 0, (const int*)touched.p, (const int*)pos.p, d->glob2loc.p, d->loc2glob.p,
+           (const double*)ctx->xq.p, xq_l.p, (const unsigned int*)mask.p, d->rank, d->owned.p, mask_l.p, d->nq_g);
+    // swap the ctx over to the local sub-mesh
+    CU(d->node_q_g.alloc(nn));
+    CU(cudaMemcpyAsync(d->node_q_g.p, ctx->node_q.p, nn * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(ctx, k_remap, div_up(nn, 256), 256, 0, (const int*)d->node_q_g.p, (const int*)d->glob2loc.p, ctx->node_q.p, nn);   // node -> LOCAL dof-node
+    CU(ctx->cq.alloc(ne_l * npc));
+    LAUNCH(ctx, k_remap, div_up(ne_l * npc, 256), 256, 0, (const int*)cq_tmp.p, (const int*)d->glob2loc.p, ctx->cq.p, ne_l * npc);
+    CU(ctx->xq.alloc(3 * nq_l));
+    CU(cudaMemcpyAsync(ctx->xq.p, xq_l.p, 3 * nq_l * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    // interface maps (host-built from the local rank masks)
+    std::vector<unsigned int> hm(nq_l);
+    CU(cudaMemcpyAsync(hm.data(), mask_l.p, nq_l * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->ne = ne_l; ctx->nq = (int)nq_l;
+    ctx->owned = d->owned.p; ctx->glob2loc = d->glob2loc.p; ctx->n_global = 3 * (i64)d->nq_g;
+    const unsigned int me = 1u << d->rank;
+    d->nbr.clear(); d->nbr_count.clear(); d->nbr_off.clear();
+    std::vector<int> cnt(d->nranks, 0);
+    int n_if = 0;
+    for (i64 l = 0; l < nq_l; l++) {
+        unsigned int m = hm[l] & ~me;
+        if (!m) continue;
+        n_if++;
+        for (int r = 0; r < d->nranks; r++) if (m & (1u << r)) cnt[r]++;
+    }
+    std::vector<int> slot_of_rank(d->nranks, -1);
+    int off = 0;
+    for (int r = 0; r < d->nranks; r++) if (cnt[r]) { slot_of_rank[r] = (int)d->nbr.size(); d->nbr.push_back(r); d->nbr_count.push_back(cnt[r]); d->nbr_off.push_back(off); off += cnt[r]; }
+    d->n_shared_total = off; d->n_if = n_if;
+    std::vector<int> send_nodes(off), fill(d->nbr.size(), 0), if_node(n_if), if_ptr(n_if + 1), if_src;
+    if_src.reserve((size_t)off + n_if);
+    int ii = 0;
+    for (i64 l = 0; l < nq_l; l++) {
+        unsigned int m = hm[l];
+        if (!(m & ~me)) continue;
+        if_node[ii] = (int)l; if_ptr[ii] = (int)if_src.size();
+        for (int r = 0; r < d->nranks; r++) {
+            if (!(m & (1u << r))) continue;
+            if (r == d->rank) { if_src.push_back(-1); continue; }
+            int s = slot_of_rank[r];
+            int p = d->nbr_off[s] + fill[s]++;          // ascending local id = ascending global id on both sides
+            send_nodes[p] = (int)l;
+            if_src.push_back(p);
+        }
+        ii++;
+    }
+    if_ptr[n_if] = (int)if_src.size();
+    CU(d->send_nodes.alloc(off)); CU(d->sendbuf.alloc(3 * (size_t)off)); CU(d->recvbuf.alloc(3 * (size_t)off));
+    CU(d->if_node.alloc(n_if)); CU(d->if_ptr.alloc(n_if + 1)); CU(d->if_src.alloc(if_src.size()));
+    if (off) CU(cudaMemcpy(d->send_nodes.p, send_nodes.data(), off * sizeof(int), cudaMemcpyHostToDevice));
+    if (n_if) {
+        CU(cudaMemcpy(d->if_node.p, if_node.data(), n_if * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d->if_src.p, if_src.data(), if_src.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(d->if_ptr.p, if_ptr.data(), (n_if + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->have_dofs = true; ctx->have_pattern = ctx->have_contrib = ctx->have_K = false;
+    return TOE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// interface sum
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_pack(const int* __restrict__ send_nodes, const double* __restrict__ y, double* __restrict__ buf, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * n) return;
+    int s = i / 3, c = i - 3 * s;
+    buf[i] = y[3 * (size_t)send_nodes[s] + c];
+}
+__global__ void k_unpack_sum(const int* __restrict__ if_node, const int* __restrict__ if_ptr, const int* __restrict__ if_src,
+                             const double* __restrict__ recv, double* __restrict__ y, int n_if) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * n_if) return;
+    int k = i / 3, c = i - 3 * k;
+    size_t dof = 3 * (size_t)if_node[k] + c;
+    double own = y[dof], s = 0.0;
+    for (int j = if_ptr[k]; j < if_ptr[k + 1]; j++) { int src = if_src[j]; s += src < 0 ? own : recv[3 * (size_t)src + c]; }   // ascending rank order
+    y[dof] = s;
+}
+
+int dist_post_spmv(toe_ctx* ctx, double* y) {
+    DistState* d = ctx->dist;
+    if (!d || d->nranks == 1 || d->n_shared_total == 0 || !y) return TOE_OK;
+    int n = d->n_shared_total;
+    LAUNCH(ctx, k_pack, div_up(3 * (i64)n, 256), 256, 0, (const int*)d->send_nodes.p, (const double*)y, d->sendbuf.p, n);
+    NC(g_nccl.GroupStart());
+    for (size_t k = 0; k < d->nbr.size(); k++) {
+        NC(g_nccl.Send(d->sendbuf.p + 3 * (size_t)d->nbr_off[k], 3 * (size_t)d->nbr_count[k], ncclDouble, d->nbr[k], d->comm, ctx->stream));
+        NC(g_nccl.Recv(d->recvbuf.p + 3 * (size_t)d->nbr_off[k], 3 * (size_t)d->nbr_count[k], ncclDouble, d->nbr[k], d->comm, ctx->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    LAUNCH(ctx, k_unpack_sum, div_up(3 * (i64)d->n_if, 256), 256, 0, (const int*)d->if_node.p, (const int*)d->if_ptr.p, (const int*)d->if_src.p,
+           (const double*)d->recvbuf.p, y, d->n_if);
+    return TOE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// global <-> local vectors (Ferrite dof order at the ABI)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_scatter_owned(const int* __restrict__ loc2glob, const unsigned char* __restrict__ owned, const double* __restrict__ local,
+                                double* __restrict__ global, int nq_l) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * nq_l) return;
+    int l = i / 3, c = i - 3 * l;
+    if (owned[l]) global[3 * (size_t)loc2glob[l] + c] = local[i];
+}
+__global__ void k_gather_local(const int* __restrict__ loc2glob, const double* __restrict__ global, double* __restrict__ local, int nq_l) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * nq_l) return;
+    int l = i / 3, c = i - 3 * l;
+    local[i] = global[3 * (size_t)loc2glob[l] + c];
+}
+__global__ void k_scatter_cells(const int* __restrict__ eloc2glob, const double* __restrict__ local, double* __restrict__ global, i64 ne_l, int width) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ne_l * width) return;
+    i64 j = i / width; int w = (int)(i - j * width);
+    global[(size_t)eloc2glob[j] * width + w] = local[i];
+}
+__global__ void k_gather_cells(const int* __restrict__ eloc2glob, const double* __restrict__ global, double* __restrict__ local, i64 ne_l) {
+    i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < ne_l) local[j] = global[eloc2glob[j]];
+}
+
+int dist_gather_vector(toe_ctx* ctx, const double* local_dev, double* global_host) {
+    DistState* d = ctx->dist;
+    size_t ng = 3 * (size_t)d->nq_g;
+    CU(d->gvec.alloc(ng));
+    CU(cudaMemsetAsync(d->gvec.p, 0, ng * sizeof(double), ctx->stream));
+    LAUNCH(ctx, k_scatter_owned, div_up(3 * (i64)ctx->nq, 256), 256, 0, (const int*)d->loc2glob.p, (const unsigned char*)d->owned.p, local_dev, d->gvec.p, ctx->nq);
+    if (d->nranks > 1) NC(g_nccl.AllReduce(d->gvec.p, d->gvec.p, ng, ncclDouble, ncclSum, d->comm, ctx->stream));
+    CU(cudaMemcpyAsync(global_host, d->gvec.p, ng * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TOE_OK;
+}
+
+int dist_scatter_vector(toe_ctx* ctx, const double* global_host, double* local_dev) {
+    DistState* d = ctx->dist;
+    size_t ng = 3 * (size_t)d->nq_g;
+    CU(d->gvec.alloc(ng));
+    CU(cudaMemcpyAsync(d->gvec.p, global_host, ng * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_gather_local, div_up(3 * (i64)ctx->nq, 256), 256, 0, (const int*)d->loc2glob.p, (const double*)d->gvec.p, local_dev, ctx->nq);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TOE_OK;
+}
+
+int dist_sum_per_element_w(toe_ctx* ctx, const double* local_dev, double* global_host, int width);
+int dist_sum_per_element(toe_ctx* ctx, const double* local_dev, double* global_host) { return dist_sum_per_element_w(ctx, local_dev, global_host, 1); }
+
+int dist_sum_per_element_w(toe_ctx* ctx, const double* local_dev, double* global_host, int width) {
+    DistState* d = ctx->dist;
+    size_t ng = (size_t)d->ne_g * width;
+    CU(d->gvec.alloc(ng));
+    CU(cudaMemsetAsync(d->gvec.p, 0, ng * sizeof(double), ctx->stream));
+    LAUNCH(ctx, k_scatter_cells, div_up(ctx->ne * width, 256), 256, 0, (const int*)d->eloc2glob.p, local_dev, d->gvec.p, ctx->ne, width);
+    if (d->nranks > 1) NC(g_nccl.AllReduce(d->gvec.p, d->gvec.p, ng, ncclDouble, ncclSum, d->comm, ctx->stream));
+    CU(cudaMemcpyAsync(global_host, d->gvec.p, ng * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TOE_OK;
+}
+
+// per-cell input given in global cell order (densities, Lamé fields) -> local device array
+int dist_localize_cells(toe_ctx* ctx, const double* global_host, double* local_dev) {
+    DistState* d = ctx->dist;
+    size_t ng = (size_t)d->ne_g;
+    CU(d->gvec.alloc(ng));
+    CU(cudaMemcpyAsync(d->gvec.p, global_host, ng * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_gather_cells, div_up(ctx->ne, 256), 256, 0, (const int*)d->eloc2glob.p, (const double*)d->gvec.p, local_dev, ctx->ne);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TOE_OK;
+}
+
+int dist_node_dofs(toe_ctx* ctx, const int** node_q_g) { *node_q_g = ctx->dist->node_q_g.p; return TOE_OK; }
+
+int dist_get_partition(toe_ctx* ctx, int32_t* part) {
+    DistState* d = ctx->dist;
+    if (!d || !d->part.p) return toe_fail(ctx, TOE_ERR_STATE, "no partition: call toe_set_mesh_distributed first");
+    CU(cudaMemcpy(part, d->part.p, d->ne_g * sizeof(int), cudaMemcpyDeviceToHost));
+    return TOE_OK;
+}
+
+int dist_local_sizes(toe_ctx* ctx, int64_t* a, int64_t* b, int64_t* c, int64_t* e) {
+    if (a) *a = ctx->ne; if (b) *b = 3 * (int64_t)ctx->nq; if (c) *c = 9 * ctx->nnzb;
+    if (e) *e = ctx->dist ? 3 * (int64_t)ctx->dist->n_if : 0;
+    return TOE_OK;
+}
+
+i64 dist_global_ne(toe_ctx* ctx) { return ctx->dist ? ctx->dist->ne_g : ctx->ne; }
+i64 dist_global_ndofs(toe_ctx* ctx) { return ctx->dist ? 3 * (i64)ctx->dist->nq_g : 3 * (i64)ctx->nq; }
+
+// global arg-max over ranks of a per-rank (value, local cell) pair; ties go to the smallest global cell id
+int dist_argmax(toe_ctx* ctx, double* max_inout, i64* cell_inout) {
+    DistState* d = ctx->dist;
+    int gl = 0;
+    CU(cudaMemcpy(&gl, d->eloc2glob.p + *cell_inout, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<double> h(2 * d->nranks, 0.0);
+    h[2 * d->rank] = *max_inout; h[2 * d->rank + 1] = (double)gl;
+    DevBuf<double> buf; CU(buf.alloc(h.size()));
+    CU(cudaMemcpyAsync(buf.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (d->nranks > 1) NC(g_nccl.AllReduce(buf.p, buf.p, h.size(), ncclDouble, ncclSum, d->comm, ctx->stream));
+    CU(cudaMemcpyAsync(h.data(), buf.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    double best = -1.0; i64 arg = 0;
+    for (int r = 0; r < d->nranks; r++) {
+        double v = h[2 * r]; i64 a = (i64)h[2 * r + 1];
+        if (v > best || (v == best && a < arg)) { best = v; arg = a; }
+    }
+    *max_inout = best; *cell_inout = arg;
+    return TOE_OK;
+}

@@ -6,6 +6,7 @@
 // energy lines FiniteElementAnalysis.jl:550 / :851, RobustSolver.jl:604 / :717; calculate_stresses :440-509 / :730-801.
 #include "element.cuh"
 #include <cmath>
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------------------
 // PCG scalar recurrences (device side)
@@ -88,11 +89,11 @@ template <bool CG>
 __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* __restrict__ blk_ptr, const int* __restrict__ blk_col,
                                                                     const double* __restrict__ val, i64 ldv,
                                                                     const double* __restrict__ x, double* __restrict__ y, int nq, int R,
-                                                                    CGScalars* cg, double* partials, unsigned int* counter) {
+                                                                    const int* done_flag, CGScalars* cg, double* partials, unsigned int* counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* bars = reinterpret_cast<u64*>(smem_raw + SPMV_STAGES * SPMV_STAGE_BYTES);      // full[0..S), empty[0..S)
     double* red = reinterpret_cast<double*>(bars + 2 * SPMV_STAGES);
-    if (CG) { if (cg->done) return; }
+    if (done_flag && *done_flag) return;
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < SPMV_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + SPMV_STAGES + s), 1); }
@@ -198,10 +199,10 @@ template <int NPC, bool CG, bool MASK>
 __global__ void __launch_bounds__(128) k_ebe_gather(const int* __restrict__ inc_ptr, const int* __restrict__ inc, const int* __restrict__ cq,
                                                     const double* __restrict__ xq, Material mat,
                                                     const unsigned char* __restrict__ dflag, const double* __restrict__ dval, int any_dirichlet,
-                                                    const double* __restrict__ x, double* __restrict__ y, int nq,
-                                                    CGScalars* cg, double* partials, unsigned int* counter) {
+                                                    const unsigned char* __restrict__ owned, const double* __restrict__ x, double* __restrict__ y, int nq,
+                                                    const int* done_flag, CGScalars* cg, double* partials, unsigned int* counter) {
     __shared__ double red[32];
-    if (CG) { if (cg->done) return; }
+    if (done_flag && *done_flag) return;
     int qn = blockIdx.x * blockDim.x + threadIdx.x;
     double dotv = 0.0;
     if (qn < nq) {
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(128) k_ebe_gather(const int* __restrict__ inc_
         double xs[3]; load3(x, qn, xs);
         if (any_dirichlet) {
 #pragma unroll
-            for (int c2 = 0; c2 < 3; c2++) { size_t d = 3 * (size_t)qn + c2; if (dflag[d]) ya[c2] = dval[d] * xs[c2]; }
+            for (int c2 = 0; c2 < 3; c2++) { size_t d = 3 * (size_t)qn + c2; if (dflag[d]) ya[c2] = (!owned || owned[qn]) ? dval[d] * xs[c2] : 0.0; }
         }
 #pragma unroll
         for (int c2 = 0; c2 < 3; c2++) y[3 * (size_t)qn + c2] = ya[c2];
@@ -290,7 +291,8 @@ double op_bytes(toe_ctx* ctx, int matrix_free) {
 }
 
 // y = A x.  cg != null: PCG mode (early exit on cg->done, fused p'Ap).  assume_masked: x is zero on prescribed dofs.
-static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, CGScalars* cg, bool assume_masked) {
+static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, CGScalars* cg, bool assume_masked, const int* done_flag = nullptr) {
+    if (cg && !done_flag) done_flag = &cg->done;
     if (!matrix_free) {
         if (!ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "assembled operator requested but K is not assembled");
         if (ctx->max_deg > SPMV_CAP) return toe_fail(ctx, TOE_ERR_MESH, "a node has %d neighbours; the SpMV stages at most %d blocks per row", ctx->max_deg, SPMV_CAP);
@@ -305,9 +307,9 @@ static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, 
             attr_set = true;
         }
         if (cg) LAUNCH(ctx, k_spmv_bsr_pipe<true>, grid, SPMV_PTHREADS, SPMV_PSMEM, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
-                       ctx->ldv, x, y, ctx->nq, R, cg, ctx->partials.p, ctx->counters.p + 1);
+                       ctx->ldv, x, y, ctx->nq, R, done_flag, cg, ctx->partials.p, ctx->counters.p + 1);
         else    LAUNCH(ctx, k_spmv_bsr_pipe<false>, grid, SPMV_PTHREADS, SPMV_PSMEM, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
-                       ctx->ldv, x, y, ctx->nq, R, (CGScalars*)nullptr, (double*)nullptr, (unsigned int*)nullptr);
+                       ctx->ldv, x, y, ctx->nq, R, done_flag, (CGScalars*)nullptr, (double*)nullptr, (unsigned int*)nullptr);
         return TOE_OK;
     }
     if (ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "matrix-free operator requested but no material is set");
@@ -315,7 +317,7 @@ static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, 
     unsigned grid = div_up(ctx->nq, 128);
     bool mask = ctx->any_dirichlet && !assume_masked;
 #define EBE_ARGS (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, \
-        (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, (int)ctx->any_dirichlet, x, y, ctx->nq, cg, ctx->partials.p, ctx->counters.p + 1
+        (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, (int)ctx->any_dirichlet, ctx->owned, x, y, ctx->nq, done_flag, cg, ctx->partials.p, ctx->counters.p + 1
     if (ctx->npc == 4) {
         if (cg) { if (mask) LAUNCH(ctx, (k_ebe_gather<4, true, true>), grid, 128, 0, EBE_ARGS); else LAUNCH(ctx, (k_ebe_gather<4, true, false>), grid, 128, 0, EBE_ARGS); }
         else    { if (mask) LAUNCH(ctx, (k_ebe_gather<4, false, true>), grid, 128, 0, EBE_ARGS); else LAUNCH(ctx, (k_ebe_gather<4, false, false>), grid, 128, 0, EBE_ARGS); }
@@ -342,7 +344,8 @@ static unsigned vec_grid(size_t n) { return min_u(div_up((i64)n, VEC_THREADS), (
 __global__ void __launch_bounds__(VEC_THREADS) k_cg_init(const double* __restrict__ f, const double* __restrict__ diag, double* __restrict__ Minv,
                                                          double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, size_t n,
                                                          CGScalars* cg, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap,
-                                                         double* partials, unsigned int* counter) {
+                                                         double* partials, unsigned int* counter,
+                                                         const unsigned char* __restrict__ owned, double* local_out) {
     __shared__ double red[32];
     double s = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -350,11 +353,12 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_init(const double* __restric
         if (fabs(d) < 1e-12) d = 1.0;
         double mi = 1.0 / d, ri = f[i], zi = mi * ri;
         Minv[i] = mi; x[i] = 0.0; r[i] = ri; p[i] = zi;
-        s += ri * zi;
+        if (!owned || owned[i / 3]) s += ri * zi;
     }
     s = block_sum(s, red);
     double tot;
     if (grid_sum_last_block(s, partials, counter, red, &tot)) {
+        if (local_out) { *local_out = tot; return; }       // partitioned: the host allreduces, k_fin_init closes
         cg->gamma = tot; cg->pAp = 0.0; cg->beta = 0.0;
         cg->res0 = sqrt(tot);
         cg->eps = atol + rtol * cg->res0;
@@ -369,7 +373,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_init(const double* __restric
 // α = γ/p'Ap, x += α p, r -= α Ap, γ' = r' M r; the last block closes the iteration (β, convergence test)
 __global__ void __launch_bounds__(VEC_THREADS) k_cg_xr(const double* __restrict__ p, const double* __restrict__ Ap, const double* __restrict__ Minv,
                                                        double* __restrict__ x, double* __restrict__ r, size_t n, CGScalars* cg,
-                                                       double* hist, i64 hist_cap, double* partials, unsigned int* counter) {
+                                                       double* hist, i64 hist_cap, double* partials, unsigned int* counter,
+                                                       const unsigned char* __restrict__ owned, double* local_out) {
     __shared__ double red[32];
     if (cg->done) return;
     const double alpha = cg->gamma / cg->pAp;
@@ -379,11 +384,13 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_xr(const double* __restrict_
         x[i] += alpha * pi;
         double ri = r[i] - alpha * Ap[i];
         r[i] = ri;
-        s += ri * ri * Minv[i];
+        if (!owned || owned[i / 3]) s += ri * ri * Minv[i];
     }
     s = block_sum(s, red);
     double tot;
-    if (grid_sum_last_block(s, partials, counter, red, &tot)) cg_after_gamma(cg, tot, hist, hist_cap);
+    if (grid_sum_last_block(s, partials, counter, red, &tot)) {
+        if (local_out) *local_out = tot; else cg_after_gamma(cg, tot, hist, hist_cap);
+    }
 }
 
 // p = M r + β p
@@ -397,10 +404,11 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_p(const double* __restrict__
 
 // out[0] = Σ (a-b)^2, out[1] = Σ a^2, out[2] = Σ a*b
 __global__ void __launch_bounds__(VEC_THREADS) k_norms(const double* __restrict__ a, const double* __restrict__ b, size_t n, double* out,
-                                                       double* partials, unsigned int* counter) {
+                                                       double* partials, unsigned int* counter, const unsigned char* __restrict__ owned) {
     __shared__ double red[32];
     double s0 = 0, s1 = 0, s2 = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (owned && !owned[i / 3]) continue;
         double ai = a[i], bi = b[i], d = ai - bi;
         s0 += d * d; s1 += ai * ai; s2 += ai * bi;
     }
@@ -413,21 +421,69 @@ __global__ void __launch_bounds__(VEC_THREADS) k_norms(const double* __restrict_
     if (grid_sum_last_block(s2, partials + 2 * gridDim.x, counter + 2, red, &tot)) out[2] = tot;
 }
 
-static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap) {
-    TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, ctx->cgs.p, true));
-    LAUNCH(ctx, k_cg_xr, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p,
-           ctx->u.p, ctx->r.p, n, ctx->cgs.p, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p + 2);
-    LAUNCH(ctx, k_cg_p, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->Minv.p, ctx->p.p, n, (const CGScalars*)ctx->cgs.p);
-    return TOE_OK;
+// ---- distributed closing kernels: the host allreduces the scalar in between ---------------------------------------
+__global__ void k_fin_init(CGScalars* cg, const double* g, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap) {
+    if (threadIdx.x || blockIdx.x) return;
+    double tot = *g;
+    cg->gamma = tot; cg->pAp = 0.0; cg->beta = 0.0;
+    cg->res0 = sqrt(tot);
+    cg->eps = atol + rtol * cg->res0;
+    cg->iter = 0; cg->itmax = itmax;
+    cg->converged = (cg->res0 <= cg->eps) ? 1 : 0;
+    cg->done = (cg->converged || itmax <= 0) ? 1 : 0;
+    cg->breakdown = 0;
+    if (hist_cap > 0) hist[0] = cg->res0;
+}
+__global__ void k_fin_pAp(CGScalars* cg, const double* v) {
+    if (threadIdx.x || blockIdx.x || cg->done) return;
+    cg_after_pAp(cg, *v);
+}
+__global__ void k_fin_gamma(CGScalars* cg, const double* v, double* hist, i64 hist_cap) {
+    if (threadIdx.x || blockIdx.x || cg->done) return;
+    cg_after_gamma(cg, *v, hist, hist_cap);
+}
+// out = Σ_owned a·b
+__global__ void __launch_bounds__(VEC_THREADS) k_dot_masked(const double* __restrict__ a, const double* __restrict__ b, size_t n,
+                                                            const unsigned char* __restrict__ owned, const int* done_flag,
+                                                            double* partials, unsigned int* counter, double* out) {
+    __shared__ double red[32];
+    if (done_flag && *done_flag) return;
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (!owned || owned[i / 3]) s += a[i] * b[i];
+    s = block_sum(s, red);
+    double tot;
+    if (grid_sum_last_block(s, partials, counter, red, &tot)) *out = tot;
 }
 
-int solve_pcg_dist(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap);  // dist.cu
+static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap) {
+    CGScalars* cg = ctx->cgs.p;
+    if (!ctx->dist) {
+        TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, cg, true));
+        LAUNCH(ctx, k_cg_xr, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p,
+               ctx->u.p, ctx->r.p, n, cg, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p + 2, (const unsigned char*)nullptr, (double*)nullptr);
+    } else {
+        // partitioned: local product, interface sum (NCCL send/recv), owner-masked dots closed by NCCL allreduce
+        double* loc = &cg->aux;
+        TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, nullptr, true, &cg->done));
+        TRY(dist_post_spmv(ctx, ctx->Ap.p));
+        LAUNCH(ctx, k_dot_masked, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, n, ctx->owned, (const int*)&cg->done,
+               ctx->partials.p, ctx->counters.p + 1, loc);
+        TRY(dist_allreduce(ctx, loc, 1));
+        LAUNCH(ctx, k_fin_pAp, 1, 32, 0, cg, (const double*)loc);
+        LAUNCH(ctx, k_cg_xr, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p,
+               ctx->u.p, ctx->r.p, n, cg, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p + 2, ctx->owned, loc);
+        TRY(dist_allreduce(ctx, loc, 1));
+        LAUNCH(ctx, k_fin_gamma, 1, 32, 0, cg, (const double*)loc, ctx->hist.p, hist_cap);
+    }
+    LAUNCH(ctx, k_cg_p, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->Minv.p, ctx->p.p, n, (const CGScalars*)cg);
+    return TOE_OK;
+}
 
 static const int CG_BATCH = 50;
 static const i64 HIST_CAP = 1LL << 20;
 
 int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap) {
-    if (ctx->dist) return solve_pcg_dist(ctx, atol, rtol, itmax, flags, stats, history, history_cap);
     int matrix_free = (flags & TOE_PCG_MATRIX_FREE) ? 1 : 0;
     if (!matrix_free && !ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "solve: K is not assembled (or pass TOE_PCG_MATRIX_FREE)");
     if (matrix_free && ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "solve: no material set");
@@ -439,14 +495,22 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     CU(ctx->hist.alloc(hist_cap));
     if (!ctx->cgs_host) CU(cudaMallocHost((void**)&ctx->cgs_host, sizeof(CGScalars)));
     i64 launches0 = ctx->launches;
+    const bool dist = ctx->dist != nullptr;
+    const int per_iter = dist ? 9 : 3;
 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, ctx->stream));
+    double* loc = &ctx->cgs.p->aux;
     LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
-           ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p);
+           ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, ctx->owned, dist ? loc : (double*)nullptr);
+    if (dist) {
+        TRY(dist_allreduce(ctx, loc, 1));
+        LAUNCH(ctx, k_fin_init, 1, 32, 0, ctx->cgs.p, (const double*)loc, atol, rtol, itmax, ctx->hist.p, hist_cap);
+    }
 
     bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
+    if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture stalled on this stack; direct launches for now
     i64 key = ctx->op_generation * 4 + matrix_free * 2 + 1;
     if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
         if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
@@ -466,7 +530,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     }
     i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
     for (i64 bt = 0; bt < max_batches; bt++) {
-        if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += 3 * CG_BATCH; }
+        if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += per_iter * CG_BATCH; }
         else for (int k = 0; k < CG_BATCH; k++) TRY(cg_iteration(ctx, matrix_free, n, hist_cap));
         CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -487,13 +551,15 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         stats->solve_seconds = ms * 1e-3;
         // true residual ||f - K u|| / ||f||  (RobustSolver.jl:468)
         TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
+        TRY(dist_post_spmv(ctx, ctx->tmp.p));
         double* out = ctx->partials.p + 3 * (N_SM * 8) + 8;
-        LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->tmp.p, n, out, ctx->partials.p, ctx->counters.p + 4);
+        LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->tmp.p, n, out, ctx->partials.p, ctx->counters.p + 4, ctx->owned);
+        TRY(dist_allreduce(ctx, out, 3));
         double hn[3];
         CU(cudaMemcpyAsync(hn, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         stats->rel_res_l2 = hn[1] > 0 ? sqrt(hn[0] / hn[1]) : sqrt(hn[0]);
-        // operator time: a few isolated launches
+        // operator time: a few isolated launches (local product only)
         const int reps = 5;
         cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
         TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
@@ -613,12 +679,16 @@ int energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem_
     else               LAUNCH(ctx, k_elem_energy<8>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, (const double*)ctx->u.p, eep, ne, part.p);
     LAUNCH(ctx, k_sum_strided, 1, 1024, 0, (const double*)part.p, (i64)grid, part.p + grid);
     double* out = ctx->partials.p + 3 * (N_SM * 8) + 8;
-    LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->u.p, n, out, ctx->partials.p, ctx->counters.p + 4);
+    LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->u.p, n, out, ctx->partials.p, ctx->counters.p + 4, ctx->owned);
     TRY(dist_allreduce(ctx, part.p + grid, 1));
+    TRY(dist_allreduce(ctx, out, 3));
     double h_e = 0, hn[3];
     CU(cudaMemcpyAsync(&h_e, part.p + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(hn, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (per_elem_host) CU(cudaMemcpyAsync(per_elem_host, ee.p, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (per_elem_host) {
+        if (ctx->dist) TRY(dist_sum_per_element(ctx, ee.p, per_elem_host));
+        else CU(cudaMemcpyAsync(per_elem_host, ee.p, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     TRY(T.finish());
     if (half_uKu) *half_uKu = h_e;
     if (compliance) *compliance = hn[2];
@@ -631,7 +701,8 @@ int energy_assembled(toe_ctx* ctx, double* half_uKu) {
     size_t n = 3 * (size_t)ctx->nq;
     TRY(op_apply(ctx, ctx->u.p, ctx->tmp.p, 0, nullptr, false));
     double* out = ctx->partials.p + 3 * (N_SM * 8) + 8;
-    LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->u.p, (const double*)ctx->tmp.p, n, out, ctx->partials.p, ctx->counters.p + 4);
+    LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->u.p, (const double*)ctx->tmp.p, n, out, ctx->partials.p, ctx->counters.p + 4, ctx->owned);
+    TRY(dist_allreduce(ctx, out, 3));
     double hn[3];
     CU(cudaMemcpyAsync(hn, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -736,6 +807,9 @@ __global__ void k_argmax_final(const double* __restrict__ bmax, const int* __res
     if (threadIdx.x == 0) { *omax = smax[0]; *oarg = sarg[0]; }
 }
 
+int dist_sum_per_element_w(toe_ctx* ctx, const double* local_dev, double* global_host, int width);
+int dist_argmax(toe_ctx* ctx, double* max_inout, i64* cell_inout);
+
 int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell) {
     if (!ctx->have_dofs || ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "stresses: mesh/material not set");
     TRY(ensure_vectors(ctx));
@@ -753,10 +827,16 @@ int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, 
     double hm = 0; int ha = 0;
     CU(cudaMemcpyAsync(&hm, bmax.p + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(&ha, barg.p + grid, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (sigma_host) CU(cudaMemcpyAsync(sigma_host, sig.p, (size_t)ne * nqp * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (vm_host) CU(cudaMemcpyAsync(vm_host, vm.p, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->dist) {
+        if (sigma_host) TRY(dist_sum_per_element_w(ctx, sig.p, sigma_host, nqp * 6));
+        if (vm_host) TRY(dist_sum_per_element_w(ctx, vm.p, vm_host, 1));
+    } else {
+        if (sigma_host) CU(cudaMemcpyAsync(sigma_host, sig.p, (size_t)ne * nqp * 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (vm_host) CU(cudaMemcpyAsync(vm_host, vm.p, (size_t)ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
+    if (ctx->dist) { i64 cell = ha; TRY(dist_argmax(ctx, &hm, &cell)); ha = (int)cell; }
     // reference semantics: max starts at 0.0 and cell id 0, updated only on strict > (:446-447, :492)
     if (hm > 0.0) { if (max_vm) *max_vm = hm; if (max_cell) *max_cell = (int64_t)ha + 1; }
     else { if (max_vm) *max_vm = 0.0; if (max_cell) *max_cell = 0; }
