@@ -67,7 +67,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(256) : "memory"); }
+__device__ __forceinline__ void consumer_sync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(256) : "memory"); }
 
 // Persistent, warp-specialised, 3-stage pipelined block-CSR SpMV.
 //   work item  = a chunk of `R` consecutive node rows = one contiguous slot range [s0,s1) of every value plane / blk_col
@@ -78,8 +78,9 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 //                three row products written back over the slot's entries of planes 0..2; phase 2 — one thread per
 //                scalar row sums its segment, stores y and accumulates the CG dot product p'Ap in a register.
 // One partial per CTA (≤148) reaches the deterministic last-block reduction.
-static const int SPMV_CONS = 256;
-static const int SPMV_PTHREADS = SPMV_CONS + 32;
+static const int SPMV_CONS = 256;          // threads of one consumer group
+static const int SPMV_GROUPS = 2;          // consumer groups working on alternate chunks (hides the x-gather latency of one behind the other)
+static const int SPMV_PTHREADS = SPMV_GROUPS * SPMV_CONS + 32;
 static const int SPMV_STAGES = 3;
 static const int SPMV_LDC = SPMV_CAP + 8;  // column-index slots per stage: a chunk is fetched from a 4-aligned slot, so up to CAP+4 entries land
 static const size_t SPMV_STAGE_BYTES = (size_t)9 * SPMV_LDS * sizeof(double) + SPMV_LDC * sizeof(int);
@@ -101,9 +102,9 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
     __syncthreads();
     const int nchunks = (nq + R - 1) / R;
     double dot = 0.0;
-    if (tid >= SPMV_CONS) {
+    if (tid >= SPMV_GROUPS * SPMV_CONS) {
         // ---------------- producer ----------------
-        if (tid == SPMV_CONS) {
+        if (tid == SPMV_GROUPS * SPMV_CONS) {
             const u64 pol = l2_evict_first_policy();
             int i = 0;
             for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, i++) {
@@ -129,17 +130,19 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
         }
     } else {
         // ---------------- consumers ----------------
-        const int lr = tid / 3, c = tid - 3 * lr;
+        const int group = tid / SPMV_CONS, gt = tid - group * SPMV_CONS;
+        const int lr = gt / 3, c = gt - 3 * lr;
         int i = 0;
         for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, i++) {
+            if ((i % SPMV_GROUPS) != group) continue;
             const int st = i % SPMV_STAGES;
             const unsigned ph = (unsigned)(i / SPMV_STAGES) & 1u;
             const int r0 = chunk * R, r1 = min(r0 + R, nq);
             const int s0 = __ldg(&blk_ptr[r0]), s1 = __ldg(&blk_ptr[r1]);
-            const bool has_row = (lr < r1 - r0) && (tid < 3 * R);
+            const bool has_row = (lr < r1 - r0) && (gt < 3 * R);
             int my_lo = 0, my_hi = 0;
             double xrow = 0.0;
-            const size_t row = 3 * (size_t)r0 + tid;
+            const size_t row = 3 * (size_t)r0 + gt;
             if (has_row) {
                 my_lo = __ldg(&blk_ptr[r0 + lr]); my_hi = __ldg(&blk_ptr[r0 + lr + 1]);
                 if (CG) xrow = __ldg(&x[row]);
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
             mbar_wait(smem_u32(bars + st), ph);                                  // bytes of this stage have landed
             const int hi_s = s1 - base;
             // all x gathers of this thread's (up to 4) slots are issued before any product is formed
-            const int k0 = s0 - base + tid;
+            const int k0 = s0 - base + gt;
             double xs[4][3];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
                     sval[k] = p0; sval[SPMV_LDS + k] = p1; sval[2 * SPMV_LDS + k] = p2;   // own slot only: no cross-thread hazard
                 }
             }
-            consumer_sync();
+            consumer_sync(group);
             if (has_row) {
                 const double* pr = sval + c * SPMV_LDS - base;
                 double acc = 0.0;
@@ -178,8 +181,8 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
                 y[row] = acc;
                 if (CG) dot += acc * xrow;
             }
-            consumer_sync();
-            if (tid == 0) { fence_proxy_async(); mbar_arrive(smem_u32(bars + SPMV_STAGES + st)); }   // stage may be refilled
+            consumer_sync(group);
+            if (gt == 0) { fence_proxy_async(); mbar_arrive(smem_u32(bars + SPMV_STAGES + st)); }   // stage may be refilled
         }
     }
     if (CG) {
