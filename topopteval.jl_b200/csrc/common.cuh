@@ -69,6 +69,9 @@ struct CGScalars {
     int converged;
     int breakdown;
     int pad;
+    // single-reduction (Chronopoulos–Gear) recurrence used on partitioned runs: {γ, δ} double-buffered by iteration parity
+    double gd[2][2];
+    double alpha[2];
 };
 
 struct DistState;   // dist.cu
@@ -111,6 +114,7 @@ struct toe_ctx {
 
     // dof vectors
     DevBuf<double> f, u, r, p, Ap, Minv, diag, tmp;
+    DevBuf<double> cg_s, cg_z;    // extra vectors of the single-reduction CG (partitioned runs only)
     DevBuf<unsigned char> dflag;  // 1 = prescribed
     DevBuf<double> dval;          // m of the handler that prescribed the dof (diag entry of the constrained K)
     bool have_diag = false;       // diag holds diag of the current operator

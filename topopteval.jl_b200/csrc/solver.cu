@@ -459,25 +459,106 @@ __global__ void __launch_bounds__(VEC_THREADS) k_dot_masked(const double* __rest
     if (grid_sum_last_block(s, partials, counter, red, &tot)) *out = tot;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Partitioned runs: Chronopoulos–Gear form of the same preconditioned CG — one merged reduction {γ=r'u, δ=w'u} and hence
+// ONE ncclAllReduce per iteration (standard CG needs two).  Mathematically identical iterates; x₀=0, M=diag(K)⁻¹,
+// same stopping rule on √γ.  Scalars are double-buffered by iteration parity so that no thread reads a value another
+// thread of the same launch rewrites.
+//   k_cgcg_vec(j):  β=γ_j/γ_{j-1}, α=γ_j/(δ_j-βγ_j/α_{j-1});  p=u+βp; s=w+βs; x+=αp; r-=αs; u=Mr   (one pass over 7 vectors)
+//   operator:       w = A u  (+ interface sum)
+//   k_cgcg_dot(j):  {γ_{j+1}, δ_{j+1}} owner-masked partial sums → slot (j+1)&1 → ncclAllReduce(2 doubles)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS) k_cgcg_init(const double* __restrict__ f, const double* __restrict__ diag, double* __restrict__ Minv,
+                                                           double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                           double* __restrict__ p, double* __restrict__ s, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double d = diag[i];
+        if (fabs(d) < 1e-12) d = 1.0;
+        double mi = 1.0 / d, ri = f[i];
+        Minv[i] = mi; x[i] = 0.0; r[i] = ri; z[i] = mi * ri; p[i] = 0.0; s[i] = 0.0;
+    }
+}
+__global__ void k_cgcg_fin_init(CGScalars* cg, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap) {
+    if (threadIdx.x || blockIdx.x) return;
+    double g = cg->gd[0][0];
+    cg->gamma = g; cg->res0 = sqrt(g); cg->eps = atol + rtol * cg->res0;
+    cg->iter = 0; cg->itmax = itmax; cg->breakdown = 0; cg->beta = 0.0; cg->pAp = 0.0;
+    cg->converged = 0; cg->done = 0;
+    cg->alpha[0] = cg->alpha[1] = 1.0;
+    cg->gd[1][0] = g; cg->gd[1][1] = 0.0;
+}
+__global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restrict__ Minv, const double* __restrict__ w, double* __restrict__ z,
+                                                          double* __restrict__ p, double* __restrict__ s, double* __restrict__ x, double* __restrict__ r,
+                                                          size_t n, CGScalars* cg, int par, double* hist, i64 hist_cap) {
+    if (cg->done) return;
+    const i64 j = cg->iter;                        // advanced by k_cgcg_dot, never inside this launch
+    const double g = cg->gd[par][0], dl = cg->gd[par][1];
+    const double gprev = cg->gd[par ^ 1][0], aprev = cg->alpha[par ^ 1];
+    const bool first = (j == 0);
+    const double res = sqrt(g);
+    const bool conv = res <= cg->eps, tired = j >= cg->itmax;
+    const double beta = first ? 0.0 : g / gprev;
+    const double denom = first ? dl : dl - beta * g / aprev;       // = p'Ap in exact arithmetic
+    const bool brk = !(denom > 0.0) && !conv && !tired;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (j < hist_cap) hist[j] = res;
+        cg->gamma = g;
+        if (conv) { cg->converged = 1; cg->done = 1; }
+        else if (tired) cg->done = 1;
+        else if (brk) { cg->breakdown = 1; cg->done = 1; }
+        else cg->alpha[par] = g / denom;
+    }
+    if (conv || tired || brk) return;
+    const double alpha = g / denom;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double pi = z[i] + beta * p[i];
+        double si = w[i] + beta * s[i];
+        p[i] = pi; s[i] = si;
+        x[i] += alpha * pi;
+        double ri = r[i] - alpha * si;
+        r[i] = ri;
+        z[i] = Minv[i] * ri;
+    }
+}
+// {r'z, w'z} over owned dofs → cg->gd[slot]; also advances the iteration counter (once, by the last block)
+__global__ void __launch_bounds__(VEC_THREADS) k_cgcg_dot(const double* __restrict__ r, const double* __restrict__ z, const double* __restrict__ w, size_t n,
+                                                          const unsigned char* __restrict__ owned, CGScalars* cg, int slot, int advance,
+                                                          double* partials, unsigned int* counter) {
+    __shared__ double red[32];
+    if (cg->done) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (owned && !owned[i / 3]) continue;
+        double zi = z[i];
+        s0 += r[i] * zi; s1 += w[i] * zi;
+    }
+    double tot;
+    s0 = block_sum(s0, red);
+    if (grid_sum_last_block(s0, partials, counter, red, &tot)) cg->gd[slot][0] = tot;
+    s1 = block_sum(s1, red);
+    if (grid_sum_last_block(s1, partials + gridDim.x, counter + 1, red, &tot)) { cg->gd[slot][1] = tot; if (advance) cg->iter += 1; }
+}
+
+// one iteration of the partitioned single-reduction CG; `par` = iteration parity (baked into captured graphs)
+static int cgcg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, int par) {
+    CGScalars* cg = ctx->cgs.p;
+    double* z = ctx->cg_z.p; double* w = ctx->Ap.p;
+    LAUNCH(ctx, k_cgcg_vec, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->Minv.p, (const double*)w, z, ctx->p.p, ctx->cg_s.p, ctx->u.p, ctx->r.p,
+           n, cg, par, ctx->hist.p, hist_cap);
+    TRY(op_launch(ctx, z, w, matrix_free, nullptr, true, &cg->done));
+    TRY(dist_post_spmv(ctx, w));
+    LAUNCH(ctx, k_cgcg_dot, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)z, (const double*)w, n, ctx->owned, cg, par ^ 1, 1,
+           ctx->partials.p, ctx->counters.p + 8);
+    TRY(dist_allreduce(ctx, &cg->gd[par ^ 1][0], 2));
+    return TOE_OK;
+}
+
 static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap) {
     CGScalars* cg = ctx->cgs.p;
-    if (!ctx->dist) {
+    {
         TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, cg, true));
         LAUNCH(ctx, k_cg_xr, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p,
                ctx->u.p, ctx->r.p, n, cg, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p + 2, (const unsigned char*)nullptr, (double*)nullptr);
-    } else {
-        // partitioned: local product, interface sum (NCCL send/recv), owner-masked dots closed by NCCL allreduce
-        double* loc = &cg->aux;
-        TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, nullptr, true, &cg->done));
-        TRY(dist_post_spmv(ctx, ctx->Ap.p));
-        LAUNCH(ctx, k_dot_masked, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, n, ctx->owned, (const int*)&cg->done,
-               ctx->partials.p, ctx->counters.p + 1, loc);
-        TRY(dist_allreduce(ctx, loc, 1));
-        LAUNCH(ctx, k_fin_pAp, 1, 32, 0, cg, (const double*)loc);
-        LAUNCH(ctx, k_cg_xr, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p,
-               ctx->u.p, ctx->r.p, n, cg, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p + 2, ctx->owned, loc);
-        TRY(dist_allreduce(ctx, loc, 1));
-        LAUNCH(ctx, k_fin_gamma, 1, 32, 0, cg, (const double*)loc, ctx->hist.p, hist_cap);
     }
     LAUNCH(ctx, k_cg_p, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->Minv.p, ctx->p.p, n, (const CGScalars*)cg);
     return TOE_OK;
@@ -499,17 +580,25 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     if (!ctx->cgs_host) CU(cudaMallocHost((void**)&ctx->cgs_host, sizeof(CGScalars)));
     i64 launches0 = ctx->launches;
     const bool dist = ctx->dist != nullptr;
-    const int per_iter = dist ? 9 : 3;
+    const int per_iter = dist ? 5 : 3;
 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, ctx->stream));
-    double* loc = &ctx->cgs.p->aux;
-    LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
-           ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, ctx->owned, dist ? loc : (double*)nullptr);
-    if (dist) {
-        TRY(dist_allreduce(ctx, loc, 1));
-        LAUNCH(ctx, k_fin_init, 1, 32, 0, ctx->cgs.p, (const double*)loc, atol, rtol, itmax, ctx->hist.p, hist_cap);
+    if (!dist) {
+        LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
+               ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, (const unsigned char*)nullptr, (double*)nullptr);
+    } else {
+        CU(ctx->cg_s.alloc(n)); CU(ctx->cg_z.alloc(n));
+        CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
+        LAUNCH(ctx, k_cgcg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->cg_z.p,
+               ctx->p.p, ctx->cg_s.p, n);
+        TRY(op_launch(ctx, ctx->cg_z.p, ctx->Ap.p, matrix_free, nullptr, true));
+        TRY(dist_post_spmv(ctx, ctx->Ap.p));
+        LAUNCH(ctx, k_cgcg_dot, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->cg_z.p, (const double*)ctx->Ap.p, n, ctx->owned,
+               ctx->cgs.p, 0, 0, ctx->partials.p, ctx->counters.p + 8);
+        TRY(dist_allreduce(ctx, &ctx->cgs.p->gd[0][0], 2));
+        LAUNCH(ctx, k_cgcg_fin_init, 1, 32, 0, ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap);
     }
 
     bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
@@ -518,10 +607,10 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
         if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
         cudaGraph_t g = nullptr;
-        CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        CU(cudaStreamBeginCapture(ctx->stream, dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
         i64 l0 = ctx->launches;
         int st = TOE_OK;
-        for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = cg_iteration(ctx, matrix_free, n, hist_cap);
+        for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap);
         ctx->launches = l0;
         cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
         if (st != TOE_OK) { if (g) cudaGraphDestroy(g); return st; }
@@ -534,7 +623,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
     for (i64 bt = 0; bt < max_batches; bt++) {
         if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += per_iter * CG_BATCH; }
-        else for (int k = 0; k < CG_BATCH; k++) TRY(cg_iteration(ctx, matrix_free, n, hist_cap));
+        else for (int k = 0; k < CG_BATCH; k++) TRY(dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap));
         CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         if (ctx->cgs_host->done) break;
