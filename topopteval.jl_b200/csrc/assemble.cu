@@ -252,6 +252,13 @@ __global__ void __launch_bounds__(128) k_asm_diag(const int* __restrict__ inc_pt
     for (int k = 0; k < 9; k++) val[(size_t)k * nnzb + s] = acc[k];
 }
 
+__global__ void k_simp_lame(Material mat, double* __restrict__ lam_e, double* __restrict__ mu_e, int ne) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    double lam, mu; material_at(mat, e, lam, mu);
+    lam_e[e] = lam; mu_e[e] = mu;
+}
+
 static int check_detj(toe_ctx* ctx, const char* who) {
     int h[4];
     CU(cudaMemcpyAsync(h, ctx->errflag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -285,7 +292,14 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
         CU(cudaMemsetAsync(ctx->val.p, 0, ctx->val.bytes(), ctx->stream));   // plane padding is read (never used) by the SpMV's bulk copies
     }
     TRY(reset_detj_flag(ctx));
+    Material amat = ctx->mat;
+    if (variant == TOE_ASM_GATHER && ctx->mat.mode == MAT_SIMP) { CU(ctx->lamw.alloc(ctx->ne)); CU(ctx->muw.alloc(ctx->ne)); }
     StageTimer T(ctx, &ctx->tm.assemble);
+    if (variant == TOE_ASM_GATHER && ctx->mat.mode == MAT_SIMP) {
+        // the gather kernels visit a cell once per block it contributes to: evaluate E(ρ)=Emin+(E0-Emin)ρ^p once per cell instead
+        LAUNCH(ctx, k_simp_lame, div_up(ctx->ne, 256), 256, 0, ctx->mat, ctx->lamw.p, ctx->muw.p, (int)ctx->ne);
+        amat.mode = MAT_PERCELL; amat.lam_e = ctx->lamw.p; amat.mu_e = ctx->muw.p;
+    }
     // start_assemble(K, f): zero K and f (FiniteElementAnalysis.jl:211 / :661)
     CU(cudaMemsetAsync(ctx->f.p, 0, n * sizeof(double), ctx->stream));
     // assembling a fresh K discards constraints applied to the previous one
@@ -304,14 +318,14 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
     } else {
         if (ctx->npc == 4) {
             LAUNCH(ctx, k_asm_offdiag<4>, div_up(nnzb, 128), 128, 0, (const int*)ctx->ctr_ptr.p, (const int*)ctx->ctr.p,
-                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, nnzb, ldv);
+                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, amat, ctx->val.p, nnzb, ldv);
             LAUNCH(ctx, k_asm_diag<4>, div_up(ctx->nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->diag_slot.p,
-                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p);
+                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, amat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p);
         } else {
             LAUNCH(ctx, k_asm_offdiag<8>, div_up(nnzb, 128), 128, 0, (const int*)ctx->ctr_ptr.p, (const int*)ctx->ctr.p,
-                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, nnzb, ldv);
+                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, amat, ctx->val.p, nnzb, ldv);
             LAUNCH(ctx, k_asm_diag<8>, div_up(ctx->nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->diag_slot.p,
-                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p);
+                   (const int*)ctx->cq.p, (const double*)ctx->xq.p, amat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p);
         }
     }
     TRY(T.finish());

@@ -111,6 +111,7 @@ struct toe_ctx {
     // material
     Material mat = {};
     DevBuf<double> density, lam_e, mu_e;
+    DevBuf<double> lamw, muw;          // per-cell Lamé parameters of the current SIMP assembly (E(ρ) evaluated once per cell)
 
     // dof vectors
     DevBuf<double> f, u, r, p, Ap, Minv, diag, tmp;
