@@ -395,6 +395,24 @@ int dist_post_spmv(toe_ctx* ctx, double* y) {
     return TOE_OK;
 }
 
+// interface sum of y and allreduce of `count` scalars issued as one NCCL group (back-to-back on the wire)
+int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count) {
+    DistState* d = ctx->dist;
+    if (!d || d->nranks == 1) return TOE_OK;
+    int n = d->n_shared_total;
+    if (n) LAUNCH(ctx, k_pack, div_up(3 * (i64)n, 256), 256, 0, (const int*)d->send_nodes.p, (const double*)y, d->sendbuf.p, n);
+    NC(g_nccl.GroupStart());
+    for (size_t k = 0; k < d->nbr.size(); k++) {
+        NC(g_nccl.Send(d->sendbuf.p + 3 * (size_t)d->nbr_off[k], 3 * (size_t)d->nbr_count[k], ncclDouble, d->nbr[k], d->comm, ctx->stream));
+        NC(g_nccl.Recv(d->recvbuf.p + 3 * (size_t)d->nbr_off[k], 3 * (size_t)d->nbr_count[k], ncclDouble, d->nbr[k], d->comm, ctx->stream));
+    }
+    NC(g_nccl.AllReduce(scal, scal, (size_t)count, ncclDouble, ncclSum, d->comm, ctx->stream));
+    NC(g_nccl.GroupEnd());
+    if (n) LAUNCH(ctx, k_unpack_sum, div_up(3 * (i64)d->n_if, 256), 256, 0, (const int*)d->if_node.p, (const int*)d->if_ptr.p, (const int*)d->if_src.p,
+                  (const double*)d->recvbuf.p, y, d->n_if);
+    return TOE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // global <-> local vectors (Ferrite dof order at the ABI)
 // ---------------------------------------------------------------------------------------------------------

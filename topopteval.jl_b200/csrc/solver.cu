@@ -90,7 +90,8 @@ template <bool CG>
 __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* __restrict__ blk_ptr, const int* __restrict__ blk_col,
                                                                     const double* __restrict__ val, i64 ldv,
                                                                     const double* __restrict__ x, double* __restrict__ y, int nq, int R,
-                                                                    const int* done_flag, CGScalars* cg, double* partials, unsigned int* counter) {
+                                                                    const int* done_flag, CGScalars* cg, double* partials, unsigned int* counter,
+                                                                    double* dot_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* bars = reinterpret_cast<u64*>(smem_raw + SPMV_STAGES * SPMV_STAGE_BYTES);      // full[0..S), empty[0..S)
     double* red = reinterpret_cast<double*>(bars + 2 * SPMV_STAGES);
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
     if (CG) {
         double d = block_sum(dot, red);
         double tot;
-        if (grid_sum_last_block(d, partials, counter, red, &tot)) cg_after_pAp(cg, tot);
+        if (grid_sum_last_block(d, partials, counter, red, &tot)) { if (dot_out) *dot_out = tot; else cg_after_pAp(cg, tot); }
     }
 }
 
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(128) k_ebe_gather(const int* __restrict__ inc_
                                                     const double* __restrict__ xq, Material mat,
                                                     const unsigned char* __restrict__ dflag, const double* __restrict__ dval, int any_dirichlet,
                                                     const unsigned char* __restrict__ owned, const double* __restrict__ x, double* __restrict__ y, int nq,
-                                                    const int* done_flag, CGScalars* cg, double* partials, unsigned int* counter) {
+                                                    const int* done_flag, CGScalars* cg, double* partials, unsigned int* counter, double* dot_out) {
     __shared__ double red[32];
     if (done_flag && *done_flag) return;
     int qn = blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(128) k_ebe_gather(const int* __restrict__ inc_
     if (CG) {
         double d = block_sum(dotv, red);
         double tot;
-        if (grid_sum_last_block(d, partials, counter, red, &tot)) cg_after_pAp(cg, tot);
+        if (grid_sum_last_block(d, partials, counter, red, &tot)) { if (dot_out) *dot_out = tot; else cg_after_pAp(cg, tot); }
     }
 }
 
@@ -294,7 +295,7 @@ double op_bytes(toe_ctx* ctx, int matrix_free) {
 }
 
 // y = A x.  cg != null: PCG mode (early exit on cg->done, fused p'Ap).  assume_masked: x is zero on prescribed dofs.
-static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, CGScalars* cg, bool assume_masked, const int* done_flag = nullptr) {
+static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, CGScalars* cg, bool assume_masked, const int* done_flag = nullptr, double* dot_out = nullptr) {
     if (cg && !done_flag) done_flag = &cg->done;
     if (!matrix_free) {
         if (!ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "assembled operator requested but K is not assembled");
@@ -310,9 +311,9 @@ static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, 
             attr_set = true;
         }
         if (cg) LAUNCH(ctx, k_spmv_bsr_pipe<true>, grid, SPMV_PTHREADS, SPMV_PSMEM, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
-                       ctx->ldv, x, y, ctx->nq, R, done_flag, cg, ctx->partials.p, ctx->counters.p + 1);
+                       ctx->ldv, x, y, ctx->nq, R, done_flag, cg, ctx->partials.p, ctx->counters.p + 1, dot_out);
         else    LAUNCH(ctx, k_spmv_bsr_pipe<false>, grid, SPMV_PTHREADS, SPMV_PSMEM, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
-                       ctx->ldv, x, y, ctx->nq, R, done_flag, (CGScalars*)nullptr, (double*)nullptr, (unsigned int*)nullptr);
+                       ctx->ldv, x, y, ctx->nq, R, done_flag, (CGScalars*)nullptr, (double*)nullptr, (unsigned int*)nullptr, (double*)nullptr);
         return TOE_OK;
     }
     if (ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "matrix-free operator requested but no material is set");
@@ -320,7 +321,7 @@ static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, 
     unsigned grid = div_up(ctx->nq, 128);
     bool mask = ctx->any_dirichlet && !assume_masked;
 #define EBE_ARGS (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, \
-        (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, (int)ctx->any_dirichlet, ctx->owned, x, y, ctx->nq, done_flag, cg, ctx->partials.p, ctx->counters.p + 1
+        (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, (int)ctx->any_dirichlet, ctx->owned, x, y, ctx->nq, done_flag, cg, ctx->partials.p, ctx->counters.p + 1, dot_out
     if (ctx->npc == 4) {
         if (cg) { if (mask) LAUNCH(ctx, (k_ebe_gather<4, true, true>), grid, 128, 0, EBE_ARGS); else LAUNCH(ctx, (k_ebe_gather<4, true, false>), grid, 128, 0, EBE_ARGS); }
         else    { if (mask) LAUNCH(ctx, (k_ebe_gather<4, false, true>), grid, 128, 0, EBE_ARGS); else LAUNCH(ctx, (k_ebe_gather<4, false, false>), grid, 128, 0, EBE_ARGS); }
@@ -489,9 +490,11 @@ __global__ void k_cgcg_fin_init(CGScalars* cg, double atol, double rtol, i64 itm
 }
 __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restrict__ Minv, const double* __restrict__ w, double* __restrict__ z,
                                                           double* __restrict__ p, double* __restrict__ s, double* __restrict__ x, double* __restrict__ r,
-                                                          size_t n, CGScalars* cg, int par, double* hist, i64 hist_cap) {
+                                                          size_t n, CGScalars* cg, int par, double* hist, i64 hist_cap,
+                                                          const unsigned char* __restrict__ owned, double* partials, unsigned int* counter) {
+    __shared__ double red[32];
     if (cg->done) return;
-    const i64 j = cg->iter;                        // advanced by k_cgcg_dot, never inside this launch
+    const i64 j = cg->iter;                        // advanced once, by the last block of this launch, after every block has read it
     const double g = cg->gd[par][0], dl = cg->gd[par][1];
     const double gprev = cg->gd[par ^ 1][0], aprev = cg->alpha[par ^ 1];
     const bool first = (j == 0);
@@ -510,6 +513,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restri
     }
     if (conv || tired || brk) return;
     const double alpha = g / denom;
+    double gs = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double pi = z[i] + beta * p[i];
         double si = w[i] + beta * s[i];
@@ -517,8 +521,14 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restri
         x[i] += alpha * pi;
         double ri = r[i] - alpha * si;
         r[i] = ri;
-        z[i] = Minv[i] * ri;
+        double zi = Minv[i] * ri;
+        z[i] = zi;
+        if (!owned || owned[i / 3]) gs += ri * zi;
     }
+    // γ_{j+1} = r'Mr over owned dofs: local partial into the other parity slot (allreduced after the operator)
+    gs = block_sum(gs, red);
+    double tot;
+    if (grid_sum_last_block(gs, partials, counter, red, &tot)) { cg->gd[par ^ 1][0] = tot; cg->iter = j + 1; }
 }
 // {r'z, w'z} over owned dofs → cg->gd[slot]; also advances the iteration counter (once, by the last block)
 __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_dot(const double* __restrict__ r, const double* __restrict__ z, const double* __restrict__ w, size_t n,
@@ -539,17 +549,18 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_dot(const double* __restri
     if (grid_sum_last_block(s1, partials + gridDim.x, counter + 1, red, &tot)) { cg->gd[slot][1] = tot; if (advance) cg->iter += 1; }
 }
 
-// one iteration of the partitioned single-reduction CG; `par` = iteration parity (baked into captured graphs)
+int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count);     // dist.cu: interface sum of y + allreduce of scal in ONE NCCL group
+
+// one iteration of the partitioned single-reduction CG; `par` = iteration parity (baked into captured graphs).
+// 4 kernels + one NCCL group: the δ partial is the operator's own fused dot over ALL local rows (Σ_ranks w_local·z equals
+// w·z because z is interface-consistent), so the allreduce does not have to wait for the interface sum.
 static int cgcg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, int par) {
     CGScalars* cg = ctx->cgs.p;
     double* z = ctx->cg_z.p; double* w = ctx->Ap.p;
     LAUNCH(ctx, k_cgcg_vec, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->Minv.p, (const double*)w, z, ctx->p.p, ctx->cg_s.p, ctx->u.p, ctx->r.p,
-           n, cg, par, ctx->hist.p, hist_cap);
-    TRY(op_launch(ctx, z, w, matrix_free, nullptr, true, &cg->done));
-    TRY(dist_post_spmv(ctx, w));
-    LAUNCH(ctx, k_cgcg_dot, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)z, (const double*)w, n, ctx->owned, cg, par ^ 1, 1,
-           ctx->partials.p, ctx->counters.p + 8);
-    TRY(dist_allreduce(ctx, &cg->gd[par ^ 1][0], 2));
+           n, cg, par, ctx->hist.p, hist_cap, ctx->owned, ctx->partials.p, ctx->counters.p + 8);
+    TRY(op_launch(ctx, z, w, matrix_free, cg, true, &cg->done, &cg->gd[par ^ 1][1]));
+    TRY(dist_exchange_allreduce(ctx, w, &cg->gd[par ^ 1][0], 2));
     return TOE_OK;
 }
 
@@ -580,7 +591,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     if (!ctx->cgs_host) CU(cudaMallocHost((void**)&ctx->cgs_host, sizeof(CGScalars)));
     i64 launches0 = ctx->launches;
     const bool dist = ctx->dist != nullptr;
-    const int per_iter = dist ? 5 : 3;
+    const int per_iter = dist ? 4 : 3;
 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
@@ -593,11 +604,10 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
         LAUNCH(ctx, k_cgcg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->cg_z.p,
                ctx->p.p, ctx->cg_s.p, n);
-        TRY(op_launch(ctx, ctx->cg_z.p, ctx->Ap.p, matrix_free, nullptr, true));
-        TRY(dist_post_spmv(ctx, ctx->Ap.p));
-        LAUNCH(ctx, k_cgcg_dot, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->cg_z.p, (const double*)ctx->Ap.p, n, ctx->owned,
-               ctx->cgs.p, 0, 0, ctx->partials.p, ctx->counters.p + 8);
-        TRY(dist_allreduce(ctx, &ctx->cgs.p->gd[0][0], 2));
+        LAUNCH(ctx, k_dot_masked, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->cg_z.p, n, ctx->owned, (const int*)nullptr,
+               ctx->partials.p, ctx->counters.p + 8, &ctx->cgs.p->gd[0][0]);
+        TRY(op_launch(ctx, ctx->cg_z.p, ctx->Ap.p, matrix_free, ctx->cgs.p, true, &ctx->cgs.p->done, &ctx->cgs.p->gd[0][1]));
+        TRY(dist_exchange_allreduce(ctx, ctx->Ap.p, &ctx->cgs.p->gd[0][0], 2));
         LAUNCH(ctx, k_cgcg_fin_init, 1, 32, 0, ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap);
     }
 
