@@ -242,9 +242,10 @@ def run_b200(args, pkg):
         return st_, e_, c_, u
 
     e2e_step()                                            # one warm-up (allocations are reused afterwards)
+    e2e_steps = min(args.steps, 3)                        # bounded: the e2e arm repeats the full path incl. setup
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         st2, e2, c2, u = e2e_step()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -262,8 +263,9 @@ def run_b200(args, pkg):
                        "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (ctx.nnz * 8 / 1e9),
                        "wall_ms_per_step": 1e3 * wall_s / args.steps},
             "clocks": clocks,
-            "e2e": {"value": ne_total * args.steps / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e": {"value": ne_total * e2e_steps / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "path": "host mesh (pinned) -> toe_set_mesh -> build_dofs -> build_pattern -> assemble -> loads -> apply! -> PCG -> energy -> u to host"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_ebe_gather" if mf else "k_spmv_bsr_pipe", "bound": "hbm", "achieved": spmv_bytes / spmv_s / 1e9, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": spmv_bytes / spmv_s / 1e9 / peaks["hbm_gbs"], "traffic": profile_traffic(mf), "peak_source": peak_src,

@@ -476,3 +476,98 @@ def test_error_behaviour(pkg):
     with pytest.raises(pkg.TopOptError):
         c.apply_dirichlet(np.array([0], dtype=np.int64))
     c.close()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# edge cases
+# ----------------------------------------------------------------------------------------------------------
+def test_edge_single_cell_and_trivial_solves(ctx, pkg, fo):
+    """smallest meshes (one tet, one hex), zero right-hand side, itmax = 0, every free dof loaded."""
+    for npc in (4, 8):
+        if npc == 4:
+            pts = np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]]); cells = np.array([[1, 2, 3, 4]], dtype=np.int64)
+        else:
+            pts, cells = pkg.meshgen.cantilever(1, 1, 1, L=(1.0, 1.0, 1.0), hex=True)
+        _setup(ctx, pts, cells)
+        prob = fo.setup_problem(pts, cells)
+        assert ctx.ndofs == 3 * npc and ctx.nnz == (3 * npc) ** 2
+        ctx.assemble_lame(0.6, 0.4); fo.assemble_stiffness_matrix(prob, 0.6, 0.4)
+        assert np.max(np.abs(ctx.values() - prob.nzval)) <= 1e-13 * np.abs(prob.nzval).max()
+        # zero load: converged at iteration 0 with u = 0 (Krylov: sqrt(r0'Mr0) = 0 <= atol)
+        st = ctx.solve_pcg(1e-8, 1e-8, 100)
+        assert st["niter"] == 0 and st["converged"] == 1 and np.all(ctx.solution() == 0.0)
+        # clamp three nodes, pull the others
+        nfd = ctx.node_dofs()
+        pres = np.sort((nfd[:3][:, None] + np.arange(3)[None, :]).reshape(-1))
+        ctx.add_nodal_force(np.arange(4, npc + 1), [0.3, -0.2, 0.1]); fo.apply_force(prob, np.arange(4, npc + 1), [0.3, -0.2, 0.1])
+        ctx.apply_dirichlet(pres); fo.apply_dirichlet(prob, pres)
+        st0 = ctx.solve_pcg(1e-8, 1e-8, 0)
+        assert st0["niter"] == 0 and st0["converged"] == 0
+        for mf in (False, True):
+            st = ctx.solve_pcg(1e-12, 1e-12, 1000, matrix_free=mf)
+            assert st["converged"] == 1 and rel(ctx.solution(), fo.solve_direct(prob)) <= TOL_U
+
+
+def test_edge_duplicate_load_nodes_and_repeated_solves(ctx, pkg, fo):
+    """`apply_force!` with a Vector holding a node twice adds twice (and divides by the list length); loads accumulate
+    over calls; a second solve on the same operator (graph replay) with a new right-hand side is independent of the first."""
+    pts, cells = pkg.meshgen.cantilever(8, 3, 2)
+    _setup(ctx, pts, cells)
+    prob = fo.setup_problem(pts, cells)
+    lam, mu = fo.create_material_model(2.0, 0.25)
+    ctx.assemble_lame(lam, mu); fo.assemble_stiffness_matrix(prob, lam, mu)
+    nodes = np.array([5, 9, 9, 14], dtype=np.int64)
+    ctx.add_nodal_force(nodes, [1.0, 2.0, 3.0]); fo.apply_force(prob, nodes, [1.0, 2.0, 3.0])
+    ctx.add_nodal_force(nodes[:1], [0.0, 0.0, -1.0]); fo.apply_force(prob, nodes[:1], [0.0, 0.0, -1.0])
+    assert np.max(np.abs(ctx.rhs() - prob.f)) <= 1e-15
+    fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0)
+    pres = fo.fixed_boundary_dofs(prob, fixed)
+    ctx.apply_dirichlet(pres); fo.apply_dirichlet(prob, pres)
+    st1 = ctx.solve_pcg(1e-11, 1e-11, 50000)
+    u1 = ctx.solution()
+    assert rel(u1, fo.solve_direct(prob)) <= TOL_U
+    f2 = np.random.default_rng(11).standard_normal(ctx.ndofs); f2[pres - 1] = 0.0
+    ctx.set_rhs(f2); prob.f[:] = f2
+    st2 = ctx.solve_pcg(1e-11, 1e-11, 50000)
+    assert st2["converged"] == 1 and rel(ctx.solution(), fo.solve_direct(prob)) <= TOL_U
+    ctx.set_rhs(np.zeros(ctx.ndofs))
+    assert ctx.solve_pcg(1e-8, 1e-8, 10)["niter"] == 0
+
+
+def test_edge_sliding_boundary_and_void_material(ctx, pkg, fo):
+    """apply_sliding_boundary! (a subset of components fixed) together with a clamp; densities of exactly 0 and 1."""
+    pts, cells = pkg.meshgen.cantilever(6, 3, 2)
+    rho = np.where(np.arange(cells.shape[0]) % 5 == 0, 0.0, 1.0)
+    grid = pkg.Grid(pts, cells, 10)
+    mm = pkg.create_simp_material_model(1.0, 0.3, 1e-8, 3.0)
+    dh, cv, K, f = pkg.setup_problem(grid, ctx=ctx)
+    pkg.assemble_stiffness_matrix_simp(K, f, dh, cv, mm, rho)
+    ch1 = pkg.apply_fixed_boundary(K, f, dh, pkg.meshgen.nodes_at_plane(pts, 0, 0.0))
+    ch2 = pkg.apply_sliding_boundary(K, f, dh, pkg.meshgen.nodes_at_plane(pts, 2, 0.0), [3])
+    pkg.apply_force(f, dh, pkg.meshgen.nodes_at_plane(pts, 0, 60.0), [0.0, -1.0, 0.0])
+    cfg = pkg.SolverConfig(method="cg", tolerance=1e-11, max_iterations=200000, verbose=False)
+    u, energy, *_ = pkg.solve_system_robust_simp(K, f, dh, cv, mm, rho, ch1, ch2, config=cfg)
+    prob = fo.setup_problem(pts, cells)
+    fo.assemble_stiffness_matrix_simp(prob, fo.create_simp_material_model(1.0, 0.3, 1e-8, 3.0), rho)
+    fo.apply_force(prob, pkg.meshgen.nodes_at_plane(pts, 0, 60.0), [0.0, -1.0, 0.0])
+    p1 = fo.fixed_boundary_dofs(prob, pkg.meshgen.nodes_at_plane(pts, 0, 0.0))
+    p2 = fo.fixed_boundary_dofs(prob, pkg.meshgen.nodes_at_plane(pts, 2, 0.0), (3,))
+    assert np.array_equal(ch1.prescribed_dofs, p1) and np.array_equal(ch2.prescribed_dofs, p2)
+    fo.apply_dirichlet(prob, p1); fo.apply_dirichlet(prob, p2)
+    uref = fo.solve_direct(prob)
+    assert rel(u, uref) <= TOL_U and abs(energy - fo.deformation_energy(prob, uref)) <= TOL_U * energy
+
+
+def test_edge_arbitrary_material_callable(ctx, pkg, fo):
+    """assemble_stiffness_matrix_simp! with a plain callable ρ ↦ (λ, μ) (host-evaluated, per cell)."""
+    pts, cells = pkg.meshgen.cantilever(4, 2, 2, hex=True)
+    rho = np.linspace(0.2, 1.0, cells.shape[0])
+    grid = pkg.Grid(pts, cells, 12)
+    model = lambda r: (0.5 + 2.0 * r, 0.25 + r * r)
+    dh, cv, K, f = pkg.setup_problem(grid, ctx=ctx)
+    pkg.assemble_stiffness_matrix_simp(K, f, dh, cv, model, rho)
+    prob = fo.setup_problem(pts, cells)
+    fo.assemble_stiffness_matrix(prob, 0.5 + 2.0 * rho, 0.25 + rho * rho)
+    assert np.max(np.abs(K.nzval() - prob.nzval)) <= 1e-12 * np.abs(prob.nzval).max()
+    Ks = K.to_scipy()
+    assert abs(Ks - prob.K()).max() <= 1e-12 * np.abs(prob.nzval).max()

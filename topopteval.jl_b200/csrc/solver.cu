@@ -575,7 +575,7 @@ static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap) {
     return TOE_OK;
 }
 
-static const int CG_BATCH = 50;
+static const int CG_BATCH_DEFAULT = 50;       // iterations per host check / captured graph (always even: parity-indexed scalars)
 static const i64 HIST_CAP = 1LL << 20;
 
 int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap) {
@@ -592,6 +592,8 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     i64 launches0 = ctx->launches;
     const bool dist = ctx->dist != nullptr;
     const int per_iter = dist ? 4 : 3;
+    int CG_BATCH = CG_BATCH_DEFAULT;
+    if (const char* eb = getenv("TOE_CG_BATCH")) { int v = atoi(eb); if (v >= 2) CG_BATCH = v & ~1; }
 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
@@ -613,7 +615,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
 
     bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
     if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture stalled on this stack; direct launches for now
-    i64 key = ctx->op_generation * 4 + matrix_free * 2 + 1;
+    i64 key = (ctx->op_generation * 4 + matrix_free * 2 + 1) * 4096 + CG_BATCH;
     if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
         if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
         cudaGraph_t g = nullptr;
