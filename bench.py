@@ -242,6 +242,7 @@ def run_b200(args, pkg):
         return st_, e_, c_, u
 
     e2e_step()                                            # one warm-up (allocations are reused afterwards)
+    tm_setup = ctx.timings()
     e2e_steps = min(args.steps, 3)                        # bounded: the e2e arm repeats the full path incl. setup
     barrier()
     t0 = time.perf_counter()
@@ -260,6 +261,7 @@ def run_b200(args, pkg):
             "config": {"workload": "%s: structured-tet cantilever %dx%dx%d cubes x 6 = %d Tet4, %d DOFs, nnz %d; E=1, nu=0.3, solid densities, clamp x=0, "
                                    "tip load -1 z; Jacobi-PCG atol=rtol=1e-8 (Krylov.jl M-norm)" % ((args.workload,) + dims + (ne_total, ctx.ndofs, ctx.nnz)),
                        "operator": "matrix-free EbE" if mf else "assembled block-CSR", "parallelism": "dd%d" % world,
+                       "exchange": ctx.comm_info()["transport"],
                        "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (ctx.nnz * 8 / 1e9),
                        "wall_ms_per_step": 1e3 * wall_s / args.steps},
             "clocks": clocks,
@@ -275,7 +277,8 @@ def run_b200(args, pkg):
                        "assemble_ms": 1e3 * stage_acc["assemble"] / args.steps, "pcg_seconds": stage_acc["solve"] / args.steps,
                        "pcg_iterations": int(st["niter"]), "pcg_converged": bool(st["converged"]), "pcg_rel_res_l2": st["rel_res_l2"],
                        "spmv_gbs": spmv_bytes / spmv_s / 1e9, "energy_ms": 1e3 * stage_acc["energy"] / args.steps,
-                       "energy": e, "compliance": c, "local_sizes": sizes},
+                       "energy": e, "compliance": c, "local_sizes": sizes,
+                       "setup_ms": {k: 1e3 * tm_setup[k] for k in ("set_mesh", "build_dofs", "build_pattern")}},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_step(pkg, CPU_SAMPLE)

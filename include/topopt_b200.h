@@ -159,6 +159,9 @@ int toe_set_mesh_distributed(toe_ctx* ctx, int64_t nn, const double* xyz, int64_
 /* part id (0-based) of every global cell (ne int32) — identical on all ranks */
 int toe_get_partition(toe_ctx* ctx, int32_t* part_of_cell);
 int toe_local_sizes(toe_ctx* ctx, int64_t* ne_local, int64_t* ndofs_local, int64_t* nnz_local, int64_t* n_interface_dofs);
+/* transport of the per-iteration interface exchange: 0 = single GPU, 1 = NCCL send/recv + allreduce,
+ * 2 = fused peer-memory kernel (CUDA IPC mailboxes over NVLink/NVSwitch; chosen when every rank can map every peer) */
+int toe_comm_info(toe_ctx* ctx, int* nranks, int* rank, int* transport);
 
 #ifdef __cplusplus
 }

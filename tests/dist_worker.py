@@ -63,6 +63,7 @@ def main():
     ctx = pkg.parallel.create_distributed_context(dist, local_rank)
     for mf in (False, True):
         results[("dist", mf)] = run(ctx, True, mf)
+    info = ctx.comm_info()
     part = ctx.partition()
     sizes = ctx.local_sizes()
     x = np.random.default_rng(5).standard_normal(ctx.ndofs)
@@ -75,7 +76,9 @@ def main():
         y_single = single.spmv(x)
         single.close()
         counts = np.bincount(part, minlength=world)
-        print("partition sizes", counts.tolist(), "local sizes rank0", sizes)
+        print("partition sizes", counts.tolist(), "local sizes rank0", sizes, "transport", info["transport"])
+        want = os.environ.get("TOE_EXPECT_TRANSPORT")
+        assert want is None or info["transport"] == want, info
         assert counts.max() - counts.min() <= 1, counts
         for mf in (False, True):
             r = results[("dist", mf)]

@@ -36,6 +36,15 @@ def test_two_gpu_partition_invariance(dims, extra):
 
 
 @pytest.mark.gpu
+def test_two_gpu_nccl_transport_gives_identical_results():
+    """the NCCL send/recv + allreduce path (peer-memory exchange disabled) must pass the same parity bars"""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, ["tests/dist_worker.py", "24,8,4"], 29535, env={"TOE_DIST_NO_P2P": "1", "TOE_EXPECT_TRANSPORT": "nccl"})
+    assert r.returncode == 0 and "DIST PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
 def test_four_gpu_partition_invariance():
     if _ngpus() < 4:
         pytest.skip("needs 4 GPUs")

@@ -84,6 +84,7 @@ SIGNATURES = {
     "toe_set_mesh_distributed": (C.c_int, [_P, C.c_int64, _D, C.c_int64, C.c_int, _I64]),
     "toe_get_partition": (C.c_int, [_P, _I32]),
     "toe_local_sizes": (C.c_int, [_P, _I64, _I64, _I64, _I64]),
+    "toe_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 
 _lib = None
@@ -344,6 +345,11 @@ class Context:
         out = np.empty(self.ne, dtype=np.int32)
         self._ck(self.lib.toe_get_partition(self.h, out.ctypes.data_as(_I32)))
         return out
+
+    def comm_info(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.toe_comm_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"nranks": a.value, "rank": b.value, "transport": {0: "single-gpu", 1: "nccl", 2: "peer-memory"}[c.value]}
 
     def local_sizes(self):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()

@@ -28,6 +28,7 @@ int dist_gather_solution(toe_ctx* ctx, double* u_host);
 int dist_scatter_vector(toe_ctx* ctx, const double* global_host, double* local_dev);
 int dist_gather_vector(toe_ctx* ctx, const double* local_dev, double* global_host);
 bool dist_active(toe_ctx* ctx);
+int dist_info(toe_ctx* ctx, int* nranks, int* rank, int* transport);
 int dist_localize_cells(toe_ctx* ctx, const double* global_host, double* local_dev);
 int dist_node_dofs(toe_ctx* ctx, const int** node_q_g);
 i64 dist_global_ne(toe_ctx* ctx);
@@ -307,6 +308,7 @@ int toe_set_mesh_distributed(toe_ctx* ctx, int64_t nn, const double* xyz, int64_
     return T.finish();
 }
 int toe_get_partition(toe_ctx* ctx, int32_t* part_of_cell) { GUARD(ctx); if (!part_of_cell) return TOE_ERR_ARG; return dist_get_partition(ctx, part_of_cell); }
+int toe_comm_info(toe_ctx* ctx, int* nranks, int* rank, int* transport) { if (!ctx) return TOE_ERR_ARG; return dist_info(ctx, nranks, rank, transport); }
 int toe_local_sizes(toe_ctx* ctx, int64_t* ne_local, int64_t* ndofs_local, int64_t* nnz_local, int64_t* n_interface_dofs) {
     GUARD(ctx); return dist_local_sizes(ctx, ne_local, ndofs_local, nnz_local, n_interface_dofs);
 }

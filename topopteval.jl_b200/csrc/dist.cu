@@ -66,12 +66,39 @@ struct DistState {
     DevBuf<double> sendbuf, recvbuf;      // 3 * n_shared_total
     DevBuf<int> if_node, if_ptr, if_src;  // unpack CSR: for interface node i, sources in ascending rank order; src = -1 → own value, else recv slot
     DevBuf<double> gvec;                  // global-length scratch for gathers
+    // peer-memory exchange (CUDA IPC over NVLink/NVSwitch): one kernel does pack + interface sum + scalar allreduce
+    bool p2p_ok = false;
+    char* mbox = nullptr;                 // this rank's mailbox: flags | scalars | receive areas (written by the peers)
+    size_t mbox_bytes = 0;
+    i64 stride3 = 0;                      // doubles per (parity, source rank) receive area
+    std::vector<char*> peer_mbox;         // [nranks] device pointers (own entry = mbox)
+    DevBuf<char*> peer_mbox_dev;
+    DevBuf<int> seg_rank, seg_off, seg_cnt, if_srcx;
+    u64 xseq = 0;                         // exchange sequence number (identical on all ranks)
+    DevBuf<u64> gbar;                     // grid-barrier counter of the exchange kernel (monotonic)
+    u64 xlaunch = 0;                      // launches of the exchange kernel so far (local)
 };
+
+static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host);
 
 bool dist_active(toe_ctx* ctx) { return ctx->dist != nullptr; }
 
+static void mailbox_close_peers(DistState* d) {
+    for (int r = 0; r < (int)d->peer_mbox.size(); r++)
+        if (r != d->rank && d->peer_mbox[r]) cudaIpcCloseMemHandle(d->peer_mbox[r]);
+    d->peer_mbox.clear();
+    d->p2p_ok = false;
+}
+static void mailbox_free_own(DistState* d) {
+    if (d->mbox) cudaFree(d->mbox);
+    d->mbox = nullptr; d->mbox_bytes = 0;
+}
+static void mailbox_release(DistState* d) { mailbox_close_peers(d); mailbox_free_own(d); }
+
 void dist_destroy(toe_ctx* ctx) {
     if (!ctx->dist) return;
+    cudaStreamSynchronize(ctx->stream);
+    mailbox_release(ctx->dist);
     if (ctx->dist->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->dist->comm);
     delete ctx->dist;
     ctx->dist = nullptr; ctx->owned = nullptr; ctx->glob2loc = nullptr; ctx->n_global = 0;
@@ -356,6 +383,9 @@ int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, cons
     }
     CU(cudaMemcpy(d->if_ptr.p, if_ptr.data(), (n_if + 1) * sizeof(int), cudaMemcpyHostToDevice));
     ctx->have_dofs = true; ctx->have_pattern = ctx->have_contrib = ctx->have_K = false;
+    TRY(ensure_vectors(ctx));                       // the exchange kernel reads the PCG `done` flag
+    CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
+    TRY(mailbox_setup(ctx, d, if_src));
     return TOE_OK;
 }
 
@@ -395,10 +425,190 @@ int dist_post_spmv(toe_ctx* ctx, double* y) {
     return TOE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused exchange over NVLink peer memory (no NCCL on the iteration path).  Every rank owns a mailbox that its peers
+// map through CUDA IPC:   [ flags u64[32] | scalars double[2][32][2] | receive areas double[2][nranks][stride3] ]
+// One single-CTA kernel per operator application:
+//   1. stores this rank's interface values of y straight into each neighbour's receive area (peer stores over NVLink),
+//      and its two partial dot products into every rank's scalar slots;
+//   2. __threadfence_system(), then publishes the sequence number in every peer's flag word;
+//   3. spins (with a time-out) until every peer's flag has reached the sequence number;
+//   4. sums the scalars in rank order (bit-identical on all ranks) and the interface contributions in ascending rank
+//      order (own value included) — the same arithmetic as the NCCL path, so results do not depend on the transport.
+// Buffers alternate with the parity of the sequence number: a rank can run at most one exchange ahead of a peer.
+// ---------------------------------------------------------------------------------------------------------
+static const size_t MB_OFF_FLAG = 0, MB_OFF_SCAL = 256, MB_OFF_RECV = 256 + 2 * 32 * 2 * sizeof(double);
+
+static const int XCHG_CTAS = 32, XCHG_THREADS = 256;      // all co-resident (the stream is otherwise idle while it runs)
+
+// software grid barrier on a monotonically increasing counter (every CTA adds 1 per barrier)
+__device__ __forceinline__ void xchg_grid_barrier(u64* ctr, u64 target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1ULL);
+        while (*reinterpret_cast<volatile u64*>(ctr) < target) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(XCHG_THREADS) k_xchg(char* const* __restrict__ peers, int nranks, int me, u64 seq, i64 stride3,
+                                                      const int* __restrict__ seg_rank, const int* __restrict__ seg_off, const int* __restrict__ seg_cnt, int nseg,
+                                                      int n_send, const int* __restrict__ send_nodes, const int* __restrict__ if_node,
+                                                      const int* __restrict__ if_ptr, const int* __restrict__ if_srcx, int n_if, double* __restrict__ y,
+                                                      double* scal, int nscal, int* done_flag, int* err_flag, u64* gbar, u64 launch_index) {
+    const u64 base = launch_index * 2ULL * gridDim.x;
+    if (done_flag && *done_flag) {                         // keep the barrier counter in step with the launch index
+        if (threadIdx.x == 0) atomicAdd(gbar, 2ULL);
+        return;
+    }
+    const int tid = threadIdx.x, gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    const int par = (int)(seq & 1);
+    char* mine = peers[me];
+    // 1. halo push: this rank's interface values straight into each neighbour's receive area (peer stores over NVLink)
+    for (int i = gtid; i < 3 * n_send; i += gsz) {
+        int p = i / 3, c = i - 3 * p;
+        int k = 0;
+        while (k + 1 < nseg && p >= seg_off[k + 1]) k++;
+        double* dst = reinterpret_cast<double*>(peers[seg_rank[k]] + MB_OFF_RECV) + ((size_t)par * nranks + me) * stride3;
+        dst[3 * (size_t)(p - seg_off[k]) + c] = y[3 * (size_t)send_nodes[p] + c];
+    }
+    if (blockIdx.x == 0 && tid < nranks && nscal > 0) {
+        double* dst = reinterpret_cast<double*>(peers[tid] + MB_OFF_SCAL) + ((size_t)par * 32 + me) * 2;
+        dst[0] = scal[0]; dst[1] = nscal > 1 ? scal[1] : 0.0;
+    }
+    __threadfence_system();
+    xchg_grid_barrier(gbar, base + gridDim.x);
+    // 2. publish the sequence number in every peer's flag word, 3. wait for every peer's
+    if (blockIdx.x == 0) {
+        if (tid < nranks && tid != me) {
+            volatile u64* out = reinterpret_cast<volatile u64*>(peers[tid] + MB_OFF_FLAG) + me;
+            *out = seq;
+            volatile u64* in = reinterpret_cast<volatile u64*>(mine + MB_OFF_FLAG) + tid;
+            long long t0 = clock64();
+            while (*in < seq) {
+                if (clock64() - t0 > 6000000000LL) { atomicExch(err_flag, 1); if (done_flag) atomicExch(done_flag, 1); break; }   // ≈3 s: a peer never arrived → stop the solve
+            }
+        }
+        __syncthreads();
+        __threadfence_system();
+    }
+    xchg_grid_barrier(gbar, base + 2ULL * gridDim.x);
+    // 4. scalars in rank order (bit-identical on all ranks)
+    if (blockIdx.x == 0 && tid == 0 && nscal > 0) {
+        const double* sc = reinterpret_cast<const double*>(mine + MB_OFF_SCAL) + (size_t)par * 32 * 2;
+        double s0 = 0.0, s1 = 0.0;
+        for (int r = 0; r < nranks; r++) { s0 += __ldcv(sc + 2 * r); s1 += __ldcv(sc + 2 * r + 1); }
+        scal[0] = s0; if (nscal > 1) scal[1] = s1;
+    }
+    // interface sum, ascending rank order
+    const double* recv = reinterpret_cast<const double*>(mine + MB_OFF_RECV) + (size_t)par * nranks * stride3;
+    for (int i = gtid; i < 3 * n_if; i += gsz) {
+        int k = i / 3, c = i - 3 * k;
+        size_t dof = 3 * (size_t)if_node[k] + c;
+        double own = y[dof], s = 0.0;
+        for (int j = if_ptr[k]; j < if_ptr[k + 1]; j++) { int src = if_srcx[j]; s += src < 0 ? own : __ldcv(recv + 3 * (size_t)src + c); }
+        y[dof] = s;
+    }
+}
+
+// (re)creates the mailboxes and exchanges their IPC handles; collective.  Falls back to the NCCL path on any failure.
+static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host) {
+    d->p2p_ok = false;
+    if (d->nranks == 1 || getenv("TOE_DIST_NO_P2P")) return TOE_OK;
+    // agree on the receive-area stride
+    int my_max = 1;
+    for (int c : d->nbr_count) my_max = std::max(my_max, c);
+    DevBuf<int> gm; CU(gm.alloc(2));
+    CU(cudaMemcpyAsync(gm.p, &my_max, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NC(g_nccl.AllReduce(gm.p, gm.p, 1, ncclInt, ncclMax, d->comm, ctx->stream));
+    int gmax = 0;
+    CU(cudaMemcpyAsync(&gmax, gm.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    i64 stride3 = 3 * (i64)gmax;
+    size_t need = MB_OFF_RECV + (size_t)2 * d->nranks * stride3 * sizeof(double);
+    int ok = 1;
+    if (need > d->mbox_bytes || d->peer_mbox.empty()) {
+        // everybody drops its mappings of the old mailboxes, a collective orders that, then everybody frees its own
+        mailbox_close_peers(d);
+        NC(g_nccl.AllReduce(gm.p, gm.p, 1, ncclInt, ncclMax, d->comm, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        mailbox_free_own(d);
+        size_t bytes = need + need / 2;
+        cudaIpcMemHandle_t mine_h;
+        memset(&mine_h, 0, sizeof mine_h);
+        if (cudaMalloc((void**)&d->mbox, bytes) != cudaSuccess) { ok = 0; d->mbox = nullptr; }
+        if (ok) { d->mbox_bytes = bytes; cudaMemset(d->mbox, 0, bytes); if (cudaIpcGetMemHandle(&mine_h, d->mbox) != cudaSuccess) ok = 0; }
+        cudaGetLastError();
+        // all-gather of the 64-byte handles through a byte-sum allreduce (own slot filled, the rest zero)
+        const size_t hs = sizeof(cudaIpcMemHandle_t);
+        std::vector<unsigned char> hbuf((size_t)d->nranks * hs + 8, 0);
+        if (ok) memcpy(hbuf.data() + (size_t)d->rank * hs, &mine_h, hs);
+        hbuf[(size_t)d->nranks * hs] = ok ? 0 : 1;          // failure votes
+        DevBuf<unsigned char> db; CU(db.alloc(hbuf.size()));
+        CU(cudaMemcpyAsync(db.p, hbuf.data(), hbuf.size(), cudaMemcpyHostToDevice, ctx->stream));
+        NC(g_nccl.AllReduce(db.p, db.p, hbuf.size(), ncclUint8, ncclSum, d->comm, ctx->stream));
+        CU(cudaMemcpyAsync(hbuf.data(), db.p, hbuf.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (hbuf[(size_t)d->nranks * hs] != 0) ok = 0;
+        d->peer_mbox.assign(d->nranks, nullptr);
+        if (ok) {
+            for (int r = 0; r < d->nranks && ok; r++) {
+                if (r == d->rank) { d->peer_mbox[r] = d->mbox; continue; }
+                cudaIpcMemHandle_t h; memcpy(&h, hbuf.data() + (size_t)r * hs, hs);
+                void* p = nullptr;
+                if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+                d->peer_mbox[r] = (char*)p;
+            }
+        }
+        // second vote: did every rank manage to map every peer?
+        int vote = ok ? 0 : 1;
+        CU(cudaMemcpyAsync(gm.p, &vote, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        NC(g_nccl.AllReduce(gm.p, gm.p, 1, ncclInt, ncclMax, d->comm, ctx->stream));
+        CU(cudaMemcpyAsync(&vote, gm.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (vote) { mailbox_release(d); return TOE_OK; }
+        CU(d->peer_mbox_dev.alloc(d->nranks));
+        CU(cudaMemcpy(d->peer_mbox_dev.p, d->peer_mbox.data(), d->nranks * sizeof(char*), cudaMemcpyHostToDevice));
+        d->xseq = 0;
+    }
+    d->stride3 = stride3;
+    if (!d->gbar.p) { CU(d->gbar.alloc(1)); CU(cudaMemset(d->gbar.p, 0, sizeof(u64))); d->xlaunch = 0; }
+    // send segments and receive indices in mailbox coordinates
+    int nseg = (int)d->nbr.size();
+    CU(d->seg_rank.alloc(nseg)); CU(d->seg_off.alloc(nseg)); CU(d->seg_cnt.alloc(nseg));
+    if (nseg) {
+        CU(cudaMemcpy(d->seg_rank.p, d->nbr.data(), nseg * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d->seg_off.p, d->nbr_off.data(), nseg * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d->seg_cnt.p, d->nbr_count.data(), nseg * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    std::vector<int> srcx(if_src_host.size());
+    for (size_t j = 0; j < if_src_host.size(); j++) {
+        int p = if_src_host[j];
+        if (p < 0) { srcx[j] = -1; continue; }
+        int k = 0;
+        while (k + 1 < nseg && p >= d->nbr_off[k + 1]) k++;
+        srcx[j] = d->nbr[k] * (int)(stride3 / 3) + (p - d->nbr_off[k]);
+    }
+    CU(d->if_srcx.alloc(srcx.size()));
+    if (!srcx.empty()) CU(cudaMemcpy(d->if_srcx.p, srcx.data(), srcx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    d->p2p_ok = true;
+    return TOE_OK;
+}
+
 // interface sum of y and allreduce of `count` scalars issued as one NCCL group (back-to-back on the wire)
 int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count) {
     DistState* d = ctx->dist;
     if (!d || d->nranks == 1) return TOE_OK;
+    if (d->p2p_ok && count <= 2) {
+        d->xseq++;
+        LAUNCH(ctx, k_xchg, XCHG_CTAS, XCHG_THREADS, 0, (char* const*)d->peer_mbox_dev.p, d->nranks, d->rank, d->xseq, d->stride3,
+               (const int*)d->seg_rank.p, (const int*)d->seg_off.p, (const int*)d->seg_cnt.p, (int)d->nbr.size(), d->n_shared_total,
+               (const int*)d->send_nodes.p, (const int*)d->if_node.p, (const int*)d->if_ptr.p, (const int*)d->if_srcx.p, d->n_if, y, scal, count,
+               &ctx->cgs.p->done, ctx->errflag.p + 2, d->gbar.p, d->xlaunch++);
+        return TOE_OK;
+    }
     int n = d->n_shared_total;
     if (n) LAUNCH(ctx, k_pack, div_up(3 * (i64)n, 256), 256, 0, (const int*)d->send_nodes.p, (const double*)y, d->sendbuf.p, n);
     NC(g_nccl.GroupStart());
@@ -524,5 +734,26 @@ int dist_argmax(toe_ctx* ctx, double* max_inout, i64* cell_inout) {
         if (v > best || (v == best && a < arg)) { best = v; arg = a; }
     }
     *max_inout = best; *cell_inout = arg;
+    return TOE_OK;
+}
+
+// did a peer-memory exchange give up waiting for a peer?  (checked once per solve)
+int dist_check_exchange(toe_ctx* ctx) {
+    if (!ctx->dist || !ctx->dist->p2p_ok) return TOE_OK;
+    int e = 0;
+    CU(cudaMemcpyAsync(&e, ctx->errflag.p + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (e) {
+        CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
+        return toe_fail(ctx, TOE_ERR_COMM, "peer-memory exchange timed out waiting for another rank (rank %d of %d)", ctx->dist->rank, ctx->dist->nranks);
+    }
+    return TOE_OK;
+}
+
+int dist_info(toe_ctx* ctx, int* nranks, int* rank, int* transport) {
+    DistState* d = ctx->dist;
+    if (nranks) *nranks = d ? d->nranks : 1;
+    if (rank) *rank = d ? d->rank : 0;
+    if (transport) *transport = (!d || d->nranks == 1) ? 0 : (d->p2p_ok ? 2 : 1);
     return TOE_OK;
 }

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_init(const double* __restric
     s = block_sum(s, red);
     double tot;
     if (grid_sum_last_block(s, partials, counter, red, &tot)) {
-        if (local_out) { *local_out = tot; return; }       // partitioned: the host allreduces, k_fin_init closes
+        if (local_out) { *local_out = tot; return; }       // caller closes the recurrence itself
         cg->gamma = tot; cg->pAp = 0.0; cg->beta = 0.0;
         cg->res0 = sqrt(tot);
         cg->eps = atol + rtol * cg->res0;
@@ -425,27 +425,6 @@ __global__ void __launch_bounds__(VEC_THREADS) k_norms(const double* __restrict_
     if (grid_sum_last_block(s2, partials + 2 * gridDim.x, counter + 2, red, &tot)) out[2] = tot;
 }
 
-// ---- distributed closing kernels: the host allreduces the scalar in between ---------------------------------------
-__global__ void k_fin_init(CGScalars* cg, const double* g, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap) {
-    if (threadIdx.x || blockIdx.x) return;
-    double tot = *g;
-    cg->gamma = tot; cg->pAp = 0.0; cg->beta = 0.0;
-    cg->res0 = sqrt(tot);
-    cg->eps = atol + rtol * cg->res0;
-    cg->iter = 0; cg->itmax = itmax;
-    cg->converged = (cg->res0 <= cg->eps) ? 1 : 0;
-    cg->done = (cg->converged || itmax <= 0) ? 1 : 0;
-    cg->breakdown = 0;
-    if (hist_cap > 0) hist[0] = cg->res0;
-}
-__global__ void k_fin_pAp(CGScalars* cg, const double* v) {
-    if (threadIdx.x || blockIdx.x || cg->done) return;
-    cg_after_pAp(cg, *v);
-}
-__global__ void k_fin_gamma(CGScalars* cg, const double* v, double* hist, i64 hist_cap) {
-    if (threadIdx.x || blockIdx.x || cg->done) return;
-    cg_after_gamma(cg, *v, hist, hist_cap);
-}
 // out = Σ_owned a·b
 __global__ void __launch_bounds__(VEC_THREADS) k_dot_masked(const double* __restrict__ a, const double* __restrict__ b, size_t n,
                                                             const unsigned char* __restrict__ owned, const int* done_flag,
@@ -467,7 +446,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_dot_masked(const double* __rest
 // thread of the same launch rewrites.
 //   k_cgcg_vec(j):  β=γ_j/γ_{j-1}, α=γ_j/(δ_j-βγ_j/α_{j-1});  p=u+βp; s=w+βs; x+=αp; r-=αs; u=Mr   (one pass over 7 vectors)
 //   operator:       w = A u  (+ interface sum)
-//   k_cgcg_dot(j):  {γ_{j+1}, δ_{j+1}} owner-masked partial sums → slot (j+1)&1 → ncclAllReduce(2 doubles)
+//   γ_{j+1} partial (owner-masked) is formed inside k_cgcg_vec, the δ_{j+1} partial inside the operator kernel (all local rows);
+//   both land in slot (j+1)&1 and are summed over the ranks by the exchange step (peer-memory kernel or NCCL group)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_init(const double* __restrict__ f, const double* __restrict__ diag, double* __restrict__ Minv,
                                                            double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
@@ -530,26 +510,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restri
     double tot;
     if (grid_sum_last_block(gs, partials, counter, red, &tot)) { cg->gd[par ^ 1][0] = tot; cg->iter = j + 1; }
 }
-// {r'z, w'z} over owned dofs → cg->gd[slot]; also advances the iteration counter (once, by the last block)
-__global__ void __launch_bounds__(VEC_THREADS) k_cgcg_dot(const double* __restrict__ r, const double* __restrict__ z, const double* __restrict__ w, size_t n,
-                                                          const unsigned char* __restrict__ owned, CGScalars* cg, int slot, int advance,
-                                                          double* partials, unsigned int* counter) {
-    __shared__ double red[32];
-    if (cg->done) return;
-    double s0 = 0.0, s1 = 0.0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (owned && !owned[i / 3]) continue;
-        double zi = z[i];
-        s0 += r[i] * zi; s1 += w[i] * zi;
-    }
-    double tot;
-    s0 = block_sum(s0, red);
-    if (grid_sum_last_block(s0, partials, counter, red, &tot)) cg->gd[slot][0] = tot;
-    s1 = block_sum(s1, red);
-    if (grid_sum_last_block(s1, partials + gridDim.x, counter + 1, red, &tot)) { cg->gd[slot][1] = tot; if (advance) cg->iter += 1; }
-}
-
-int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count);     // dist.cu: interface sum of y + allreduce of scal in ONE NCCL group
+int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count);
+int dist_check_exchange(toe_ctx* ctx);     // dist.cu: interface sum of y + allreduce of scal in ONE NCCL group
 
 // one iteration of the partitioned single-reduction CG; `par` = iteration parity (baked into captured graphs).
 // 4 kernels + one NCCL group: the δ partial is the operator's own fused dot over ALL local rows (Σ_ranks w_local·z equals
@@ -603,6 +565,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
                ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, (const unsigned char*)nullptr, (double*)nullptr);
     } else {
         CU(ctx->cg_s.alloc(n)); CU(ctx->cg_z.alloc(n));
+        CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
         CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
         LAUNCH(ctx, k_cgcg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->cg_z.p,
                ctx->p.p, ctx->cg_s.p, n);
@@ -647,6 +610,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     CU(cudaGetLastError());
     CGScalars h = *ctx->cgs_host;
     ctx->tm.solve = ms * 1e-3;
+    if (dist) TRY(dist_check_exchange(ctx));
     ctx->have_solution = true;
 
     if (stats) {
