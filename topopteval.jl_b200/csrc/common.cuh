@@ -105,6 +105,14 @@ struct toe_ctx {
     i64 ldv = 0;              // stride between the 9 value planes (>= nnzb, multiple of 16)
     // block -> contributing (e,a,b) lists, off-diagonal blocks only (entries e*64 + a*8 + b, ascending e)
     DevBuf<int> ctr_ptr, ctr;
+    // tiles of consecutive cells for the matrix-free operator (ebe_tile.cu)
+    bool have_tiles = false;
+    int ntiles = 0, tile_elems = 0, tile_max_nodes = 0;
+    i64 tile_slots = 0;                                   // Σ local nodes over tiles = rows of the staging array
+    DevBuf<int> tile_off, tile_nodes;                     // [ntiles+1], [tile_slots]: dof-node id of each local node
+    DevBuf<unsigned short> tile_lconn, tile_inc, tile_nstart;   // local connectivity, node-sorted ref ids, first ref of each local node
+    DevBuf<int> nst_ptr, nst;                             // node -> staging rows (ascending)
+    DevBuf<double> tile_stage;                            // 3 doubles per staging row
     // K values: 9 planes of nnzb doubles, plane k = 3*c+d holds K[3q+c, 3q'+d] of block slot s at val[k*nnzb+s]
     DevBuf<double> val;
 
@@ -218,6 +226,21 @@ __device__ __forceinline__ bool grid_sum_last_block(double block_val /*thread 0*
     return false;
 }
 
+// ---- PCG scalar recurrences (device side) -------------------------------------------------------------------
+__device__ __forceinline__ void cg_after_pAp(CGScalars* s, double pAp) {
+    s->pAp = pAp;
+    if (!(pAp > 0.0)) { s->done = 1; s->breakdown = 1; }       // Krylov.jl stops on non-positive curvature
+}
+__device__ __forceinline__ void cg_after_gamma(CGScalars* s, double gnew, double* hist, i64 hist_cap) {
+    s->beta = gnew / s->gamma;
+    s->gamma = gnew;
+    s->iter += 1;
+    double res = sqrt(gnew);
+    if (s->iter < hist_cap) hist[s->iter] = res;
+    if (res <= s->eps) { s->done = 1; s->converged = 1; }
+    else if (s->iter >= s->itmax) s->done = 1;
+}
+
 // (cell, a, b) packed into one int for the block -> contribution lists
 template <int NPC> __host__ __device__ __forceinline__ int ctr_pack(int e, int a, int b) {
     return NPC == 4 ? ((e << 4) | (a << 2) | b) : ((e << 6) | (a << 3) | b);
@@ -238,5 +261,7 @@ int op_apply(toe_ctx* ctx, const double* x, double* y, int matrix_free, double* 
 double op_bytes(toe_ctx* ctx, int matrix_free);
 int dist_post_spmv(toe_ctx* ctx, double* y);      // interface sum (no-op without dist)
 int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count);
+int mesh_build_tiles(toe_ctx* ctx);
+int ebe_tile_launch(toe_ctx* ctx, const double* x, double* y, CGScalars* cg, bool mask, const int* done_flag, double* dot_out);
 int dist_sum_per_element(toe_ctx* ctx, const double* local_dev, double* global_host);   // per-cell output, global cell order
 void dist_destroy(toe_ctx* ctx);

@@ -382,7 +382,7 @@ int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, cons
         CU(cudaMemcpy(d->if_src.p, if_src.data(), if_src.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(d->if_ptr.p, if_ptr.data(), (n_if + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    ctx->have_dofs = true; ctx->have_pattern = ctx->have_contrib = ctx->have_K = false;
+    ctx->have_dofs = true; ctx->have_pattern = ctx->have_contrib = ctx->have_K = false; ctx->have_tiles = false;
     TRY(ensure_vectors(ctx));                       // the exchange kernel reads the PCG `done` flag
     CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
     TRY(mailbox_setup(ctx, d, if_src));

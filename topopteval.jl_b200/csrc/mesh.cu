@@ -98,6 +98,7 @@ int mesh_upload(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, const 
     if (nn > 2147483647LL / 3 || ne * npc > 2147483647LL)
         return toe_fail(ctx, TOE_ERR_ARG, "mesh too large for 32-bit device indices (nn=%lld, ne=%lld)", (long long)nn, (long long)ne);
     ctx->have_mesh = ctx->have_dofs = ctx->have_pattern = ctx->have_contrib = ctx->have_K = ctx->have_solution = false;
+    ctx->have_tiles = false;
     ctx->have_diag = false; ctx->any_dirichlet = false;
     ctx->mat.mode = MAT_NONE;
     ctx->op_generation++;
@@ -169,7 +170,7 @@ int mesh_build_dofs(toe_ctx* ctx) {
     LAUNCH(ctx, k_cq, div_up(total, 256), 256, 0, (const int*)ctx->conn0.p, (const int*)ctx->node_q.p, ctx->cq.p, total);
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->have_dofs = true;
-    ctx->have_pattern = ctx->have_contrib = ctx->have_K = false;
+    ctx->have_pattern = ctx->have_contrib = ctx->have_K = false; ctx->have_tiles = false;
     return TOE_OK;
 }
 

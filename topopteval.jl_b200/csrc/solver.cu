@@ -9,23 +9,6 @@
 #include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------------------
-// PCG scalar recurrences (device side)
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cg_after_pAp(CGScalars* s, double pAp) {
-    s->pAp = pAp;
-    if (!(pAp > 0.0)) { s->done = 1; s->breakdown = 1; }       // Krylov.jl stops on non-positive curvature
-}
-__device__ __forceinline__ void cg_after_gamma(CGScalars* s, double gnew, double* hist, i64 hist_cap) {
-    s->beta = gnew / s->gamma;
-    s->gamma = gnew;
-    s->iter += 1;
-    double res = sqrt(gnew);
-    if (s->iter < hist_cap) hist[s->iter] = res;
-    if (res <= s->eps) { s->done = 1; s->converged = 1; }
-    else if (s->iter >= s->itmax) s->done = 1;
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // assembled operator: block-CSR SpMV.  A CTA owns SPMV_ROWS consecutive node rows (a contiguous range of block
 // slots).  Phase 1 streams the slots — thread t takes slot s0+t, s0+t+blockDim, … so the 9 value planes and the
 // column indices are read as fully coalesced streams — and leaves the three row products of each slot in shared
@@ -317,9 +300,11 @@ static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, 
         return TOE_OK;
     }
     if (ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "matrix-free operator requested but no material is set");
+    bool mask = ctx->any_dirichlet && !assume_masked;
+    static const bool use_gather = getenv("TOE_EBE_GATHER") != nullptr;       // older node-gather form, kept for comparison
+    if (!use_gather) return ebe_tile_launch(ctx, x, y, cg, mask, done_flag, dot_out);
     if (!ctx->have_pattern) return toe_fail(ctx, TOE_ERR_STATE, "matrix-free operator needs the incidence lists (toe_build_pattern)");
     unsigned grid = div_up(ctx->nq, 128);
-    bool mask = ctx->any_dirichlet && !assume_masked;
 #define EBE_ARGS (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, \
         (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, (int)ctx->any_dirichlet, ctx->owned, x, y, ctx->nq, done_flag, cg, ctx->partials.p, ctx->counters.p + 1, dot_out
     if (ctx->npc == 4) {
@@ -547,6 +532,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     if (itmax < 0) return toe_fail(ctx, TOE_ERR_ARG, "solve: itmax must be >= 0");
     TRY(ensure_vectors(ctx));
     TRY(compute_diag(ctx));
+    if (matrix_free && !getenv("TOE_EBE_GATHER")) TRY(mesh_build_tiles(ctx));     // allocations must not happen inside graph capture
     size_t n = 3 * (size_t)ctx->nq;
     const i64 hist_cap = HIST_CAP;            // fixed: pointer and capacity are baked into the captured graph
     CU(ctx->hist.alloc(hist_cap));
