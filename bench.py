@@ -253,6 +253,8 @@ def run_b200(args, pkg):
     h2d = pts.nbytes + cells.nbytes + load.nbytes + pres.nbytes
     d2h = u.nbytes + 2 * 8 + 128
 
+    if not st["converged"] or st["breakdown"]:
+        raise SystemExit("bench.py: PCG did not converge (niter=%d, breakdown=%d, rel_res=%g) — no number reported" % (st["niter"], st["breakdown"], st["rel_res_l2"]))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

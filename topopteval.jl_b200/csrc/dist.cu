@@ -483,11 +483,17 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_xchg(char* const* __restrict__
     // 2. publish the sequence number in every peer's flag word, 3. wait for every peer's
     if (blockIdx.x == 0) {
         if (tid < nranks && tid != me) {
-            volatile u64* out = reinterpret_cast<volatile u64*>(peers[tid] + MB_OFF_FLAG) + me;
-            *out = seq;
-            volatile u64* in = reinterpret_cast<volatile u64*>(mine + MB_OFF_FLAG) + tid;
+            // release: the grid barrier made every CTA's peer stores (each followed by a system fence) visible to this
+            // thread; this fence + st.release.sys orders them before the flag for any observer of the flag
+            __threadfence_system();
+            u64* out = reinterpret_cast<u64*>(peers[tid] + MB_OFF_FLAG) + me;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(out), "l"(seq) : "memory");
+            const u64* in = reinterpret_cast<const u64*>(mine + MB_OFF_FLAG) + tid;
             long long t0 = clock64();
-            while (*in < seq) {
+            u64 v;
+            while (true) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(in) : "memory");
+                if (v >= seq) break;
                 if (clock64() - t0 > 6000000000LL) { atomicExch(err_flag, 1); if (done_flag) atomicExch(done_flag, 1); break; }   // ≈3 s: a peer never arrived → stop the solve
             }
         }
