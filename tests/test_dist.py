@@ -31,7 +31,7 @@ def _ngpus():
 def test_two_gpu_partition_invariance(dims, extra):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, ["tests/dist_worker.py", dims] + extra, 29531)
+    r = _torchrun(2, ["tests/dist_worker.py", dims] + extra, 29531, env={"TOE_EXPECT_TRANSPORT": "nccl"})
     assert r.returncode == 0 and "DIST PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
@@ -41,16 +41,16 @@ def test_two_gpu_larger_mesh_is_reproducible():
     peer-memory exchange shows up as run-to-run differences), and parity with the single-GPU solve."""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, ["tests/dist_worker.py", "96,32,12", "repeat"], 29536, timeout=400)
+    r = _torchrun(2, ["tests/dist_worker.py", "96,32,12", "repeat"], 29536, timeout=400, env={"TOE_DIST_P2P": "1", "TOE_EXPECT_TRANSPORT": "peer-memory"})
     assert r.returncode == 0 and "DIST PARITY OK" in r.stdout and "NON-REPRODUCIBLE" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
 @pytest.mark.gpu
-def test_two_gpu_nccl_transport_gives_identical_results():
-    """the NCCL send/recv + allreduce path (peer-memory exchange disabled) must pass the same parity bars"""
+def test_two_gpu_peer_memory_transport_gives_identical_results():
+    """the opt-in fused peer-memory exchange (CUDA IPC mailboxes) must pass the same parity bars as the NCCL transport"""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, ["tests/dist_worker.py", "24,8,4"], 29535, env={"TOE_DIST_NO_P2P": "1", "TOE_EXPECT_TRANSPORT": "nccl"})
+    r = _torchrun(2, ["tests/dist_worker.py", "24,8,4"], 29535, env={"TOE_DIST_P2P": "1", "TOE_EXPECT_TRANSPORT": "peer-memory"})
     assert r.returncode == 0 and "DIST PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
