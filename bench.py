@@ -215,8 +215,10 @@ def run_b200(args, pkg):
     ne_total = cells.shape[0]
 
     # ---- device-resident arm: W warm-up steps, then exactly K timed steps -------------------------------------
-    for _ in range(args.warmup):
-        step()
+    for w in range(args.warmup):
+        stw, _, _ = step()
+        if not stw["converged"]:
+            print("bench.py: warm-up step %d did not converge (niter=%d, breakdown=%d)" % (w, stw["niter"], stw["breakdown"]), file=sys.stderr, flush=True)
     sampler = ClockSampler(local_rank)
     barrier()
     launches0 = ctx.timings()["kernel_launches"]
@@ -225,8 +227,12 @@ def run_b200(args, pkg):
     t0 = time.perf_counter()
     stage_acc = {"assemble": 0.0, "solve": 0.0, "spmv": 0.0, "energy": 0.0, "loads": 0.0, "dirichlet": 0.0}
     st = e = c = None
+    restarts = 0
     for _ in range(args.steps):
         st, e, c = step()
+        restarts += int(st.get("restarts", 0))
+        if not st["converged"] or st["breakdown"]:
+            raise SystemExit("bench.py: a timed step did not converge (niter=%d, breakdown=%d, rel_res=%g) — no number reported" % (st["niter"], st["breakdown"], st["rel_res_l2"]))
         tm = ctx.timings()
         stage_acc["assemble"] += tm["assemble"]; stage_acc["solve"] += tm["solve"]; stage_acc["energy"] += tm["energy"]
         stage_acc["loads"] += tm["loads"]; stage_acc["dirichlet"] += tm["dirichlet"]; stage_acc["spmv"] += st["spmv_seconds"]
@@ -262,9 +268,11 @@ def run_b200(args, pkg):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     # the end-to-end arm must have done the same work and reached the same answer as the device-resident arm
-    if (not st2["converged"]) or st2["niter"] != st["niter"] or abs(e2 - e) > 1e-9 * abs(e) or not np.all(np.isfinite(u)):
-        raise SystemExit("bench.py: end-to-end step disagrees with the device-resident step (iters %d vs %d, energy %r vs %r, converged %r)"
-                         % (st2["niter"], st["niter"], e2, e, bool(st2["converged"])))
+    e2e_invalid = None
+    if (not st2["converged"]) or abs(int(st2["niter"]) - int(st["niter"])) > 2 or abs(e2 - e) > 1e-8 * abs(e) or not np.all(np.isfinite(u)):
+        e2e_invalid = ("end-to-end step disagrees with the device-resident step (iters %d vs %d, energy %r vs %r, converged %r)"
+                       % (st2["niter"], st["niter"], e2, e, bool(st2["converged"])))
+        print("bench.py: " + e2e_invalid, file=sys.stderr, flush=True)
     h2d = pts.nbytes + cells.nbytes + load.nbytes + pres.nbytes
     d2h = u.nbytes + 2 * 8 + 128
 
@@ -282,7 +290,7 @@ def run_b200(args, pkg):
                        "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (ctx.nnz * 8 / 1e9),
                        "wall_ms_per_step": 1e3 * wall_s / args.steps},
             "clocks": clocks,
-            "e2e": {"value": ne_total * e2e_steps / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": None if e2e_invalid else ne_total * e2e_steps / e2e_s, "invalid": e2e_invalid, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pcg_iterations": int(st2["niter"]), "energy": e2,
                     "path": "host mesh (pinned) -> toe_set_mesh -> build_dofs -> build_pattern -> assemble -> loads -> apply! -> PCG -> energy -> u to host"},
             "gpu_launches": int(launches),
@@ -292,7 +300,7 @@ def run_b200(args, pkg):
                          "share_of_step": stage_acc["spmv"] / dev_s},
             "stages": {"assemble_elements_per_s": ne_total * args.steps / stage_acc["assemble"] if stage_acc["assemble"] > 0 else None,
                        "assemble_ms": 1e3 * stage_acc["assemble"] / args.steps, "pcg_seconds": stage_acc["solve"] / args.steps,
-                       "pcg_iterations": int(st["niter"]), "pcg_converged": bool(st["converged"]), "pcg_rel_res_l2": st["rel_res_l2"],
+                       "pcg_iterations": int(st["niter"]), "pcg_converged": bool(st["converged"]), "pcg_rel_res_l2": st["rel_res_l2"], "pcg_restarts": restarts,
                        "spmv_gbs": spmv_bytes / spmv_s / 1e9, "energy_ms": 1e3 * stage_acc["energy"] / args.steps,
                        "energy": e, "compliance": c, "local_sizes": sizes,
                        "setup_ms": {k: 1e3 * tm_setup[k] for k in ("set_mesh", "build_dofs", "build_pattern")}},

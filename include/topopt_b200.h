@@ -51,6 +51,7 @@ typedef struct toe_pcg_stats {
     double  spmv_seconds;     /* niter x average operator time, measured on a few isolated launches after the solve */
     double  spmv_bytes;       /* algorithmic bytes of one operator application */
     int64_t kernel_launches;  /* kernels launched by this call */
+    int64_t restarts;         /* partitioned runs only: solves restarted after a CG breakdown (0 normally) */
 } toe_pcg_stats;
 
 typedef struct toe_timings {  /* device seconds of the last call of each stage (CUDA events) */

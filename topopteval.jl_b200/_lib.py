@@ -20,7 +20,7 @@ class PcgStats(C.Structure):
     _fields_ = [("niter", C.c_int64), ("converged", C.c_int32), ("breakdown", C.c_int32),
                 ("res0_M", C.c_double), ("res_M", C.c_double), ("rel_res_l2", C.c_double),
                 ("solve_seconds", C.c_double), ("spmv_seconds", C.c_double), ("spmv_bytes", C.c_double),
-                ("kernel_launches", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("restarts", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -546,48 +546,55 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, ctx->stream));
-    if (!dist) {
-        LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
-               ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, (const unsigned char*)nullptr, (double*)nullptr);
-    } else {
-        CU(ctx->cg_s.alloc(n)); CU(ctx->cg_z.alloc(n));
-        CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
-        CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
-        LAUNCH(ctx, k_cgcg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->cg_z.p,
-               ctx->p.p, ctx->cg_s.p, n);
-        LAUNCH(ctx, k_dot_masked, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->cg_z.p, n, ctx->owned, (const int*)nullptr,
-               ctx->partials.p, ctx->counters.p + 8, &ctx->cgs.p->gd[0][0]);
-        TRY(op_launch(ctx, ctx->cg_z.p, ctx->Ap.p, matrix_free, ctx->cgs.p, true, &ctx->cgs.p->done, &ctx->cgs.p->gd[0][1]));
-        TRY(dist_exchange_allreduce(ctx, ctx->Ap.p, &ctx->cgs.p->gd[0][0], 2));
-        LAUNCH(ctx, k_cgcg_fin_init, 1, 32, 0, ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap);
-    }
+    // Partitioned runs: a solve that ends in a CG breakdown is restarted from x0 = 0 (at most twice) and the number of restarts is
+    // reported.  One such first solve was seen at N=2 / 10M tets on the NCCL transport (identical re-runs converge); the restart
+    // keeps the result valid while the cause is open.  TOE_DIST_NO_RETRY=1 disables it.
+    int restarts = 0;
+    for (;; restarts++) {
+        if (!dist) {
+            LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
+                   ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, (const unsigned char*)nullptr, (double*)nullptr);
+        } else {
+            CU(ctx->cg_s.alloc(n)); CU(ctx->cg_z.alloc(n));
+            CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
+            CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
+            LAUNCH(ctx, k_cgcg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->cg_z.p,
+                   ctx->p.p, ctx->cg_s.p, n);
+            LAUNCH(ctx, k_dot_masked, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->cg_z.p, n, ctx->owned, (const int*)nullptr,
+                   ctx->partials.p, ctx->counters.p + 8, &ctx->cgs.p->gd[0][0]);
+            TRY(op_launch(ctx, ctx->cg_z.p, ctx->Ap.p, matrix_free, ctx->cgs.p, true, &ctx->cgs.p->done, &ctx->cgs.p->gd[0][1]));
+            TRY(dist_exchange_allreduce(ctx, ctx->Ap.p, &ctx->cgs.p->gd[0][0], 2));
+            LAUNCH(ctx, k_cgcg_fin_init, 1, 32, 0, ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap);
+        }
 
-    bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
-    if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture stalled on this stack; direct launches for now
-    i64 key = (ctx->op_generation * 4 + matrix_free * 2 + 1) * 4096 + CG_BATCH;
-    if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
-        if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
-        cudaGraph_t g = nullptr;
-        CU(cudaStreamBeginCapture(ctx->stream, dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
-        i64 l0 = ctx->launches;
-        int st = TOE_OK;
-        for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap);
-        ctx->launches = l0;
-        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
-        if (st != TOE_OK) { if (g) cudaGraphDestroy(g); return st; }
-        if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-        ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
-        cudaGraphDestroy(g);
-        if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-        ctx->graph_key = key;
-    }
-    i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
-    for (i64 bt = 0; bt < max_batches; bt++) {
-        if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += per_iter * CG_BATCH; }
-        else for (int k = 0; k < CG_BATCH; k++) TRY(dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap));
-        CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->cgs_host->done) break;
+        bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
+        if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture stalled on this stack; direct launches for now
+        i64 key = (ctx->op_generation * 4 + matrix_free * 2 + 1) * 4096 + CG_BATCH;
+        if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
+            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            CU(cudaStreamBeginCapture(ctx->stream, dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
+            i64 l0 = ctx->launches;
+            int st = TOE_OK;
+            for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap);
+            ctx->launches = l0;
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+            if (st != TOE_OK) { if (g) cudaGraphDestroy(g); return st; }
+            if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+            ctx->graph_key = key;
+        }
+        i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
+        for (i64 bt = 0; bt < max_batches; bt++) {
+            if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += per_iter * CG_BATCH; }
+            else for (int k = 0; k < CG_BATCH; k++) TRY(dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap));
+            CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (ctx->cgs_host->done) break;
+        }
+        if (!dist || !ctx->cgs_host->breakdown || restarts >= 2 || getenv("TOE_DIST_NO_RETRY")) break;
     }
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaEventSynchronize(e1));
@@ -626,6 +633,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         stats->spmv_seconds = (double)h.iter * (oms * 1e-3 / reps);
         stats->spmv_bytes = op_bytes(ctx, matrix_free);
         stats->kernel_launches = ctx->launches - launches0;
+        stats->restarts = restarts;
     }
     if (history && history_cap > 0) {
         i64 cnt = h.iter + 1 < history_cap ? h.iter + 1 : history_cap;
