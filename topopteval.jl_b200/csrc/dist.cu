@@ -386,6 +386,9 @@ int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, cons
         CU(cudaMemcpy(d->if_src.p, if_src.data(), if_src.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(d->if_ptr.p, if_ptr.data(), (n_if + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    // the uploads above ran on the NULL stream from pageable memory (the call returns once the data is staged, the DMA may
+    // still be in flight) and ctx->stream is non-blocking: order them before anything the ctx stream does with the maps
+    CU(cudaDeviceSynchronize());
     ctx->have_dofs = true; ctx->have_pattern = ctx->have_contrib = ctx->have_K = false; ctx->have_tiles = false;
     TRY(ensure_vectors(ctx));                       // the exchange kernel reads the PCG `done` flag
     CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
@@ -630,6 +633,7 @@ static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_
     }
     CU(d->if_srcx.alloc(srcx.size()));
     if (!srcx.empty()) CU(cudaMemcpy(d->if_srcx.p, srcx.data(), srcx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());                    // NULL-stream uploads / memsets above vs the non-blocking ctx stream
     d->p2p_ok = true;
     return TOE_OK;
 }

@@ -551,6 +551,10 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     // keeps the result valid while the cause is open.  TOE_DIST_NO_RETRY=1 disables it.
     int restarts = 0;
     for (;; restarts++) {
+        if (restarts > 0) {                        // a restart recomputes the Jacobi diagonal too (its interface sum is an exchange)
+            ctx->have_diag = false;
+            TRY(compute_diag(ctx));
+        }
         if (!dist) {
             LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
                    ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, (const unsigned char*)nullptr, (double*)nullptr);
