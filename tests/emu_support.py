@@ -1,0 +1,50 @@
+"""TEST INFRASTRUCTURE — host-side emulation build of the CUDA sources (tests/cuda_emu).
+
+`emu_package()` returns the package with its ctypes handle pointing at tests/cuda_emu/_build/libtopopt_emu.so: the very same
+.cu sources compiled for fibers on the host (see tests/cuda_emu/cuda_emu.h).  It checks kernel *logic* where no GPU
+exists — indexing, initialisation (allocations come back 0xFF-filled), barriers, the mbarrier pipeline protocol, CG
+recurrences, partition / interface maps — at toy sizes.  It is never a product path: the package itself only ever loads
+libtopopt_b200.so and fails loudly without a B200; nothing here is timed or shipped."""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
+EMU_LIB = os.path.join(EMU_DIR, "_build", "libtopopt_emu.so")
+
+
+def build_emu(extra: str = "", opt: str = "-O2") -> str:
+    res = subprocess.run(["make", "-C", EMU_DIR, "-j8", "OPT=" + opt] + (["EXTRA=" + extra] if extra else []), capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libtopopt_emu.so failed:\n" + res.stdout[-3000:] + res.stderr[-6000:])
+    return EMU_LIB
+
+
+def load_emu():
+    build_emu()
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    lib = C.CDLL(EMU_LIB, mode=C.RTLD_LOCAL)
+    for name, (res, args) in pkg._lib.SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib.emu_peak_bytes.restype = C.c_size_t
+    lib.emu_live_allocations.restype = C.c_size_t
+    lib.emu_check_all_guards.restype = C.c_int
+    return pkg, lib
+
+
+@contextlib.contextmanager
+def emulated(pkg, lib):
+    """Inside the block `pkg.Context` / the api functions drive the emulated library (tests only)."""
+    saved = pkg._lib._lib
+    pkg._lib._lib = lib
+    try:
+        yield pkg
+    finally:
+        pkg._lib._lib = saved

@@ -1,0 +1,122 @@
+"""N>1 path on the host: rank THREADS drive one emulated ctx each (tests/cuda_emu; NCCL replaced by an in-process rendezvous).
+
+TEST INFRASTRUCTURE (see tests/emu_support.py): checks the logic of the partitioned path — RCB partition, interface maps,
+sub-assembled K, owner-masked dots, single-reduction CG recurrence, gathers back to the reference's DOF order — against the
+single-ctx result, with 0xFF-filled allocations so that any read-before-write shows.  The real gate is tests/test_dist.py on
+2/4 B200s."""
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import emu_support  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    pkg, lib = emu_support.load_emu()
+    with emu_support.emulated(pkg, lib):
+        yield pkg, lib
+    assert lib.emu_check_all_guards() == 0
+
+
+def _problem(pkg, dims, simp):
+    pts, cells = pkg.meshgen.cantilever(*dims)
+    rho = pkg.meshgen.simp_like_density(cells.shape[0]) if simp else None
+    fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0)
+    load = pkg.meshgen.nodes_at_plane(pts, 0, 60.0)
+    return pts, cells, rho, fixed, load
+
+
+def _run(pkg, ctx, prob, distributed, mf, tol=1e-10):
+    pts, cells, rho, fixed, load = prob
+    lam, mu = pkg.create_material_model(1.0, 0.3)
+    ctx.set_mesh(pts, cells, distributed=distributed)
+    ctx.build_dofs(); ctx.build_pattern()
+    if rho is not None:
+        (ctx.set_material_simp if mf else ctx.assemble_simp)(1.0, 0.3, 1e-8, 3.0, rho)
+    else:
+        (ctx.set_material_lame if mf else ctx.assemble_lame)(lam, mu)
+    ctx.add_nodal_force(load, [0.0, 0.0, -1.0])
+    if rho is not None:
+        ctx.add_volume_force([0.0, 0.0, -0.01], density=rho, skip_below=1e-6)
+    nfd = ctx.node_dofs()
+    pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
+    m = ctx.apply_dirichlet(pres)
+    st = ctx.solve_pcg(tol, tol, 20000, matrix_free=mf, graph=False)
+    u = ctx.solution()
+    e, c, ee = ctx.energy(per_element=True)
+    _, vm, mx, arg = ctx.stresses(False, True)
+    return dict(u=u, e=e, c=c, ee=ee, it=st["niter"], conv=st["converged"], brk=st["breakdown"], restarts=st["restarts"], m=m, f=ctx.rhs(),
+                nfd=nfd, mx=mx, arg=arg, vm=vm, diag=ctx.diagonal())
+
+
+def _run_ranks(pkg, world, prob, mf, repeats=1):
+    uid = pkg.Context.comm_unique_id()
+    out = [None] * world
+    err = [None] * world
+
+    def worker(rank):
+        try:
+            ctx = pkg.Context(rank)
+            ctx.comm_init(world, rank, uid)
+            res = []
+            for _ in range(repeats):
+                res.append(_run(pkg, ctx, prob, True, mf))
+            res[-1]["part"] = ctx.partition()
+            res[-1]["sizes"] = ctx.local_sizes()
+            res[-1]["transport"] = ctx.comm_info()["transport"]
+            x = np.random.default_rng(5).standard_normal(ctx.ndofs)
+            res[-1]["spmv"] = ctx.spmv(x, matrix_free=mf)
+            ctx.close()
+            out[rank] = res
+        except BaseException as ex:  # noqa: BLE001
+            err[rank] = ex
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(600)
+    for r, ex in enumerate(err):
+        if ex is not None:
+            raise AssertionError("rank %d failed: %r" % (r, ex))
+    assert all(o is not None for o in out), "a rank thread did not finish"
+    return out
+
+
+@pytest.mark.parametrize("world,dims,simp", [(2, (12, 4, 2), False), (2, (10, 4, 3), True), (4, (16, 4, 2), False), (4, (12, 5, 3), True), (8, (24, 4, 2), False)])
+@pytest.mark.parametrize("mf", [False, True])
+def test_partitioned_equals_single_ctx(emu, world, dims, simp, mf):
+    pkg, lib = emu
+    prob = _problem(pkg, dims, simp)
+    single = pkg.Context(0)
+    ref = _run(pkg, single, prob, False, mf)
+    x = np.random.default_rng(5).standard_normal(single.ndofs)
+    y_single = single.spmv(x, matrix_free=mf)
+    single.close()
+    assert ref["conv"] == 1
+    ranks = _run_ranks(pkg, world, prob, mf, repeats=2)
+    r0 = ranks[0][-1]
+    counts = np.bincount(r0["part"], minlength=world)
+    assert counts.max() - counts.min() <= 1, counts
+    assert r0["transport"] == "nccl"
+    for rk in range(world):
+        first, r = ranks[rk][0], ranks[rk][-1]
+        # every rank returns the same global answer, re-setups are bit-reproducible, and it equals the unpartitioned solve
+        assert np.array_equal(r["u"], r0["u"]) and r["it"] == r0["it"] and r["e"] == r0["e"]
+        assert np.array_equal(first["u"], r["u"]) and first["it"] == r["it"], "second set-up on the same ctx gave a different solve"
+        assert r["conv"] == 1 and r["brk"] == 0 and r["restarts"] == 0
+        assert np.array_equal(r["nfd"], ref["nfd"])
+        assert np.linalg.norm(r["u"] - ref["u"]) <= 1e-8 * np.linalg.norm(ref["u"])
+        assert abs(r["e"] - ref["e"]) <= 1e-8 * abs(ref["e"]) and abs(r["c"] - ref["c"]) <= 1e-8 * abs(ref["c"])
+        assert np.max(np.abs(r["ee"] - ref["ee"])) <= 1e-8 * np.max(np.abs(ref["ee"]))
+        assert np.max(np.abs(r["f"] - ref["f"])) <= 1e-12 * np.max(np.abs(ref["f"]))
+        assert np.max(np.abs(r["diag"] - ref["diag"]) / np.abs(ref["diag"])) <= 1e-12
+        assert abs(r["m"] - ref["m"]) <= 1e-12 * ref["m"]
+        assert abs(r["it"] - ref["it"]) <= max(5, ref["it"] // 50)
+        assert r["arg"] == ref["arg"] and np.max(np.abs(r["vm"] - ref["vm"])) <= 1e-7 * ref["mx"]
+        assert np.max(np.abs(r["spmv"] - y_single)) <= 1e-12 * np.max(np.abs(y_single))

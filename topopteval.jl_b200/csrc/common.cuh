@@ -160,8 +160,21 @@ inline int toe_fail(toe_ctx* c, int code, const char* fmt, ...) {
     return toe_fail(ctx, TOE_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); } while (0)
 #define TRY(call) do { int _s = (call); if (_s != TOE_OK) return _s; } while (0)
 
+#ifndef TOE_EMU
 #define LAUNCH(ctx, kern, grid, block, smem, ...) do { \
     kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+// dynamic shared memory of the running block
+#define TOE_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
+typedef unsigned smem_ptr_t;       // 32-bit shared-window address, as the mbarrier / bulk-copy PTX wants it
+#else
+// tests/cuda_emu (host-side logic check of these very sources, test infrastructure only): a launch runs the grid on fibers
+#define LAUNCH(ctx, kern, grid, block, smem, ...) do { \
+    auto _args = std::make_tuple(__VA_ARGS__); \
+    emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [_args]() { std::apply([](auto... a) { kern(a...); }, _args); }); \
+    (ctx)->launches++; } while (0)
+#define TOE_DYN_SMEM(type, name, align) type* name = reinterpret_cast<type*>(emu::dyn_smem())
+typedef size_t smem_ptr_t;
+#endif
 
 static inline unsigned int div_up(i64 a, i64 b) { return (unsigned int)((a + b - 1) / b); }
 static inline unsigned int min_u(unsigned int a, unsigned int b) { return a < b ? a : b; }

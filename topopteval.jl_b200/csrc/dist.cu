@@ -30,6 +30,15 @@ static NcclApi g_nccl;
 
 static int nccl_load(std::string& err) {
     if (g_nccl.h) return TOE_OK;
+#ifdef TOE_EMU
+    // tests/cuda_emu: rank threads of one process rendezvous through the stand-in functions (test infrastructure only)
+    (void)err;
+    g_nccl.GetUniqueId = &ncclGetUniqueId; g_nccl.CommInitRank = &ncclCommInitRank; g_nccl.CommDestroy = &ncclCommDestroy;
+    g_nccl.AllReduce = &ncclAllReduce; g_nccl.Send = &ncclSend; g_nccl.Recv = &ncclRecv; g_nccl.GroupStart = &ncclGroupStart;
+    g_nccl.GroupEnd = &ncclGroupEnd; g_nccl.GetErrorString = &ncclGetErrorString;
+    g_nccl.h = (void*)&g_nccl;
+    return TOE_OK;
+#endif
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     void* h = nullptr;
     for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
@@ -519,12 +528,20 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_xchg(char* const* __restrict__
             // thread; this fence + st.release.sys orders them before the flag for any observer of the flag
             __threadfence_system();
             u64* out = reinterpret_cast<u64*>(peers[tid] + MB_OFF_FLAG) + me;
+#ifndef TOE_EMU
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(out), "l"(seq) : "memory");
+#else
+            *reinterpret_cast<volatile u64*>(out) = seq;
+#endif
             const u64* in = reinterpret_cast<const u64*>(mine + MB_OFF_FLAG) + tid;
             long long t0 = clock64();
             u64 v;
             while (true) {
+#ifndef TOE_EMU
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(in) : "memory");
+#else
+                v = *reinterpret_cast<const volatile u64*>(in); emu::yield();
+#endif
                 if (v >= seq) break;
                 if (clock64() - t0 > 6000000000LL) { atomicExch(err_flag, 1); if (done_flag) atomicExch(done_flag, 1); break; }   // ≈3 s: a peer never arrived → stop the solve
             }

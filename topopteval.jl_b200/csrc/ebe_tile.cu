@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restr
                                                               const unsigned char* __restrict__ dflag, const double* __restrict__ x,
                                                               double* __restrict__ stage, i64 ne, const int* done_flag) {
     const int TE = TILE_REFS / NPC;
-    extern __shared__ __align__(16) double sm[];
+    TOE_DYN_SMEM(double, sm, 16);
     if (done_flag && *done_flag) return;
     const int t = blockIdx.x, tid = threadIdx.x;
     const int off = __ldg(&tile_off[t]), m = __ldg(&tile_off[t + 1]) - off;

@@ -20,15 +20,16 @@ static const int SPMV_CAP = 960;           // block slots staged per pass (multi
 static const int SPMV_LDS = SPMV_CAP + 6;  // shared-memory plane stride (even → 16-byte aligned planes; staggers the banks of the 3 product planes)
 
 // ---- sm_100a async-copy plumbing (inline PTX): mbarrier + cp.async.bulk (SASS: UBLKCP / SYNCS) ------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+#ifndef TOE_EMU
+__device__ __forceinline__ smem_ptr_t smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(smem_ptr_t bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+__device__ __forceinline__ void mbar_expect_tx(smem_ptr_t bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase) {
+__device__ __forceinline__ void mbar_wait(smem_ptr_t bar, unsigned phase) {
     unsigned ok;
     do {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
@@ -41,16 +42,28 @@ __device__ __forceinline__ u64 l2_evict_first_policy() {
     return pol;
 }
 // bytes must be a multiple of 16, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, u64 policy) {
+__device__ __forceinline__ void bulk_g2s(smem_ptr_t dst, const void* src, unsigned bytes, smem_ptr_t bar, u64 policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+__device__ __forceinline__ void mbar_arrive(smem_ptr_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void consumer_sync(int group) { asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(256) : "memory"); }
+#else
+// tests/cuda_emu: the same protocol on the host (phase / arrival / tx-byte accounting in the barrier word, immediate copies)
+static inline smem_ptr_t smem_u32(const void* p) { return (size_t)p; }
+static inline void mbar_init(smem_ptr_t bar, unsigned count) { emu::mbar_init((void*)bar, count); }
+static inline void mbar_expect_tx(smem_ptr_t bar, unsigned bytes) { emu::mbar_expect_tx((void*)bar, bytes); }
+static inline void mbar_wait(smem_ptr_t bar, unsigned phase) { emu::mbar_wait((void*)bar, phase); }
+static inline u64 l2_evict_first_policy() { return 0; }
+static inline void bulk_g2s(smem_ptr_t dst, const void* src, unsigned bytes, smem_ptr_t bar, u64) { emu::bulk_g2s((void*)dst, src, bytes, (void*)bar); }
+static inline void fence_proxy_async() {}
+static inline void mbar_arrive(smem_ptr_t bar) { emu::mbar_arrive((void*)bar); }
+static inline void consumer_sync(int group) { emu::named_barrier(group + 1, 256); }
+#endif
 
 // Persistent, warp-specialised, 3-stage pipelined block-CSR SpMV.
 //   work item  = a chunk of `R` consecutive node rows = one contiguous slot range [s0,s1) of every value plane / blk_col
@@ -75,7 +88,7 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
                                                                     const double* __restrict__ x, double* __restrict__ y, int nq, int R,
                                                                     const int* done_flag, CGScalars* cg, double* partials, unsigned int* counter,
                                                                     double* dot_out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TOE_DYN_SMEM(unsigned char, smem_raw, 128);
     u64* bars = reinterpret_cast<u64*>(smem_raw + SPMV_STAGES * SPMV_STAGE_BYTES);      // full[0..S), empty[0..S)
     double* red = reinterpret_cast<double*>(bars + 2 * SPMV_STAGES);
     if (done_flag && *done_flag) return;
@@ -101,7 +114,7 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
                 const int cnt = ((s1 - base) + 3) & ~3;
                 double* sval = reinterpret_cast<double*>(smem_raw + st * SPMV_STAGE_BYTES);
                 int* scol = reinterpret_cast<int*>(sval + 9 * SPMV_LDS);
-                const unsigned full = smem_u32(bars + st);
+                const smem_ptr_t full = smem_u32(bars + st);
                 if (cnt > 0) {
                     mbar_expect_tx(full, (unsigned)cnt * (9 * 8 + 4));
 #pragma unroll
