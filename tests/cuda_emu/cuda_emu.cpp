@@ -71,7 +71,10 @@ struct Rank {                      // per OS thread (= per emulated GPU / ctx dr
     std::vector<Fiber> fibers;
     void* sched_sp = nullptr;
     int cur = -1;
-    BlockState bs;
+    BlockState bs0;
+    BlockState* bs = &bs0;                 // state of the block the running fiber belongs to
+    std::vector<BlockState> co_bs;         // co-resident launches: one state per block
+    bool next_coresident = false;
     const std::function<void()>* body = nullptr;
     char* dyn = nullptr; size_t dyn_cap = 0;
     long long clk = 0;
@@ -119,13 +122,48 @@ void fiber_prepare(Rank& r, int t) {
     f.done = false;
 }
 
-void run_block(Rank& r, unsigned b, unsigned T, size_t smem) {
-    blockIdx.x = b;
-    BlockState& bs = r.bs;
+void block_state_init(BlockState& bs, unsigned T) {
     bs.nthreads = T; bs.live = T; bs.bar_arrived = 0; bs.bar_gen = 0;
     for (int k = 0; k < 16; k++) { bs.nb_arrived[k] = 0; bs.nb_gen[k] = 0; }
     unsigned nw = (T + 31) / 32;
     for (unsigned w = 0; w < nw; w++) { bs.warps[w].arrived = 0; bs.warps[w].gen = 0; bs.warps[w].live = (w + 1) * 32 <= T ? 32 : T - w * 32; }
+}
+
+// all blocks of the grid resident at once (kernels with a software grid barrier); such kernels must not use __shared__
+void run_grid_coresident(Rank& r, unsigned grid, unsigned T) {
+    r.co_bs.resize(grid);
+    for (unsigned b = 0; b < grid; b++) block_state_init(r.co_bs[b], T);
+    unsigned total = grid * T;
+    for (unsigned i = 0; i < total; i++) fiber_prepare(r, (int)i);
+    unsigned remaining = total;
+    unsigned long long idle_passes = 0;
+    while (remaining > 0) {
+        unsigned long long p0 = r.progress;
+        for (unsigned i = 0; i < total; i++) {
+            Fiber& f = r.fibers[i];
+            if (f.done) continue;
+            unsigned b = i / T, t = i - b * T;
+            r.cur = (int)i; blockIdx.x = b; threadIdx.x = t; r.bs = &r.co_bs[b];
+            emu_switch(&r.sched_sp, f.sp);
+            if (f.done) { remaining--; r.co_bs[b].live--; r.co_bs[b].warps[t / 32].live--; }
+        }
+        if (r.progress == p0) {
+            if (++idle_passes > 200000000ULL) {
+                fprintf(stderr, "cuda_emu: DEADLOCK in a co-resident %u x %u kernel (%u threads never finished)\n", grid, T, remaining);
+                r.last_error = 719;
+                for (unsigned i = 0; i < total; i++) r.fibers[i].done = true;
+                break;
+            }
+        } else idle_passes = 0;
+    }
+    r.bs = &r.bs0;
+}
+
+void run_block(Rank& r, unsigned b, unsigned T, size_t smem) {
+    blockIdx.x = b;
+    BlockState& bs = r.bs0;
+    r.bs = &bs;
+    block_state_init(bs, T);
     if (smem) memset(r.dyn, 0xCD, smem);                 // uninitialised dynamic shared memory is garbage, not zeros
     for (unsigned t = 0; t < T; t++) fiber_prepare(r, (int)t);
     unsigned remaining = T;
@@ -156,7 +194,8 @@ void run_grid(Rank& r, unsigned grid, unsigned block, size_t smem, const std::fu
     if (smem > r.dyn_cap) { free(r.dyn); r.dyn = nullptr; if (posix_memalign((void**)&r.dyn, 1024, smem + 1024)) abort(); r.dyn_cap = smem; }
     gridDim.x = grid; blockDim.x = block;
     r.body = &body;
-    for (unsigned b = 0; b < grid && !r.deadlock; b++) run_block(r, b, block, smem);
+    if (r.next_coresident) { r.next_coresident = false; run_grid_coresident(r, grid, block); }
+    else for (unsigned b = 0; b < grid && !r.deadlock; b++) run_block(r, b, block, smem);
     r.body = nullptr; r.cur = -1;
     r.deadlock = false;
 }
@@ -170,9 +209,19 @@ void launch(unsigned grid, unsigned block, size_t smem, std::function<void()> bo
     run_grid(r, grid, block, smem, body);
 }
 void* dyn_smem() { return g_rank->dyn; }
-void yield() { Rank& r = *g_rank; Fiber& f = r.fibers[r.cur]; emu_switch(&f.sp, r.sched_sp); }
+void next_launch_coresident() { rank_state().next_coresident = true; }
+static thread_local unsigned g_jitter_state = 12345u;
+void yield() {
+    Rank& r = *g_rank; Fiber& f = r.fibers[r.cur];
+    static const bool jitter = getenv("EMU_JITTER") != nullptr;          // perturbs the interleaving of rank threads
+    if (jitter && r.bs != &r.bs0) {            // only inside co-resident (exchange) kernels
+        g_jitter_state = g_jitter_state * 1664525u + 1013904223u;
+        if ((g_jitter_state >> 20) % 257 == 0) { struct timespec ts = {0, (long)((g_jitter_state >> 8) % 200000)}; nanosleep(&ts, nullptr); }
+    }
+    emu_switch(&f.sp, r.sched_sp);
+}
 void sync_threads() {
-    Rank& r = *g_rank; BlockState& bs = r.bs;
+    Rank& r = *g_rank; BlockState& bs = *r.bs;
     unsigned long long g = bs.bar_gen;
     bs.bar_arrived++;
     for (;;) {
@@ -182,7 +231,7 @@ void sync_threads() {
     }
 }
 void named_barrier(int id, int count) {
-    Rank& r = *g_rank; BlockState& bs = r.bs;
+    Rank& r = *g_rank; BlockState& bs = *r.bs;
     unsigned long long g = bs.nb_gen[id];
     bs.nb_arrived[id]++;
     for (;;) {
@@ -194,7 +243,7 @@ void named_barrier(int id, int count) {
 unsigned long long shfl(unsigned long long v, int src_lane) {
     Rank& r = *g_rank;
     unsigned t = threadIdx.x;
-    Warp& w = r.bs.warps[t / 32];
+    Warp& w = r.bs->warps[t / 32];
     unsigned long long g = w.gen;
     int buf = (int)(g & 1);
     w.slot[buf][t & 31] = v;
@@ -374,8 +423,9 @@ cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t) {
     for (auto& n : g->nodes) run_grid(r, n.grid, n.block, n.smem, n.body);
     return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// rank threads share one address space: the handle simply carries the pointer
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); h->reserved[16] = 1; return cudaSuccess; }
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { if (h.reserved[16] != 1) return cudaErrorInvalidValue; memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 }  // extern "C"

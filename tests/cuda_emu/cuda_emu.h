@@ -105,6 +105,7 @@ namespace emu {
 void launch(unsigned grid, unsigned block, size_t smem, std::function<void()> body);   // runs (or records, during capture) the grid
 void* dyn_smem();                          // dynamic shared memory of the running block
 void yield();                              // cooperative reschedule (used by spin loops)
+void next_launch_coresident();             // the next launch runs all its blocks at once (software grid barrier inside)
 void sync_threads();
 void named_barrier(int id, int count);
 unsigned long long shfl(unsigned long long v, int src_lane);   // warp exchange: returns the value `src_lane` deposited
@@ -113,8 +114,8 @@ long long clock();
 
 // ---- device intrinsics ----------------------------------------------------------------------------------------------
 static inline void __syncthreads() { emu::sync_threads(); }
-static inline void __threadfence() {}
-static inline void __threadfence_system() {}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline long long clock64() { return emu::clock(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }

@@ -54,7 +54,7 @@ def _run(pkg, ctx, prob, distributed, mf, tol=1e-10):
                 nfd=nfd, mx=mx, arg=arg, vm=vm, diag=ctx.diagonal())
 
 
-def _run_ranks(pkg, world, prob, mf, repeats=1):
+def _run_ranks(pkg, world, prob, mf, repeats=1, tol=1e-10):
     uid = pkg.Context.comm_unique_id()
     out = [None] * world
     err = [None] * world
@@ -65,7 +65,7 @@ def _run_ranks(pkg, world, prob, mf, repeats=1):
             ctx.comm_init(world, rank, uid)
             res = []
             for _ in range(repeats):
-                res.append(_run(pkg, ctx, prob, True, mf))
+                res.append(_run(pkg, ctx, prob, True, mf, tol))
             res[-1]["part"] = ctx.partition()
             res[-1]["sizes"] = ctx.local_sizes()
             res[-1]["transport"] = ctx.comm_info()["transport"]
@@ -120,3 +120,22 @@ def test_partitioned_equals_single_ctx(emu, world, dims, simp, mf):
         assert abs(r["it"] - ref["it"]) <= max(5, ref["it"] // 50)
         assert r["arg"] == ref["arg"] and np.max(np.abs(r["vm"] - ref["vm"])) <= 1e-7 * ref["mx"]
         assert np.max(np.abs(r["spmv"] - y_single)) <= 1e-12 * np.max(np.abs(y_single))
+
+
+@pytest.mark.parametrize("world,dims", [(2, (12, 4, 2)), (4, (16, 4, 2)), (8, (24, 4, 2))])
+def test_peer_memory_exchange_protocol(emu, world, dims, monkeypatch):
+    """The fused peer-memory exchange kernel (mailboxes + flags + parity buffers + software grid barrier) under emulation:
+    rank threads share one address space, the kernel's CTAs run co-resident, EMU_JITTER perturbs the interleaving.
+    Results must be bit-identical to the NCCL transport (same arithmetic order) and re-set-ups must reproduce."""
+    pkg, lib = emu
+    monkeypatch.setenv("EMU_JITTER", "1")
+    prob = _problem(pkg, dims, False)
+    nccl = _run_ranks(pkg, world, prob, False, repeats=1, tol=1e-9)
+    monkeypatch.setenv("TOE_DIST_P2P", "1")
+    p2p = _run_ranks(pkg, world, prob, False, repeats=3, tol=1e-9)
+    assert p2p[0][-1]["transport"] == "peer-memory" and nccl[0][-1]["transport"] == "nccl"
+    for rk in range(world):
+        for rep in range(3):
+            r = p2p[rk][rep]
+            assert r["conv"] == 1 and r["restarts"] == 0
+            assert r["it"] == nccl[rk][0]["it"] and np.array_equal(r["u"], nccl[rk][0]["u"]), (rk, rep, r["it"], nccl[rk][0]["it"])

@@ -480,7 +480,11 @@ int dist_post_spmv(toe_ctx* ctx, double* y) {
 // ---------------------------------------------------------------------------------------------------------
 static const size_t MB_OFF_FLAG = 0, MB_OFF_SCAL = 256, MB_OFF_RECV = 256 + 2 * 32 * 2 * sizeof(double);
 
+#ifndef TOE_EMU
 static const int XCHG_CTAS = 32, XCHG_THREADS = 256;      // all co-resident (the stream is otherwise idle while it runs)
+#else
+static const int XCHG_CTAS = 4, XCHG_THREADS = 64;        // tests/cuda_emu: same protocol, fewer fibers
+#endif
 
 // software grid barrier on a monotonically increasing counter (every CTA adds 1 per barrier)
 __device__ __forceinline__ void xchg_grid_barrier(u64* ctr, u64 target) {
@@ -488,7 +492,11 @@ __device__ __forceinline__ void xchg_grid_barrier(u64* ctr, u64 target) {
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(ctr, 1ULL);
-        while (*reinterpret_cast<volatile u64*>(ctr) < target) {}
+        while (*reinterpret_cast<volatile u64*>(ctr) < target) {
+#ifdef TOE_EMU
+            emu::yield();
+#endif
+        }
         __threadfence();
     }
     __syncthreads();
@@ -661,6 +669,9 @@ int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count) {
     if (!d || d->nranks == 1) return TOE_OK;
     if (d->p2p_ok && count <= 2) {
         d->xseq++;
+#ifdef TOE_EMU
+        emu::next_launch_coresident();
+#endif
         LAUNCH(ctx, k_xchg, XCHG_CTAS, XCHG_THREADS, 0, (char* const*)d->peer_mbox_dev.p, d->nranks, d->rank, d->xseq, d->stride3,
                (const int*)d->seg_rank.p, (const int*)d->seg_off.p, (const int*)d->seg_cnt.p, (int)d->nbr.size(), d->n_shared_total,
                (const int*)d->send_nodes.p, (const int*)d->if_node.p, (const int*)d->if_ptr.p, (const int*)d->if_srcx.p, d->n_if, y, scal, count,
