@@ -1,0 +1,177 @@
+"""Size-independent properties of the hot path on the synthetic structured-tet cantilever (BASELINE.json configs C3/C4).
+
+At 1M / 10M tets the CPU oracle cannot restate the whole path in test time, so parity at full size is pinned through
+properties that hold at any size (and that the oracle satisfies too — tests/test_emu_fullsize.py runs this very function at
+toy sizes against the emulated build and against the oracle):
+
+  * DOF map: bit-exact against the vectorised first-touch restatement (Ferrite close!(dh), FiniteElementAnalysis.jl:174-176)
+  * pattern size: closed form for the 6-tet split (nodes + 2·edges blocks), structure checks on the downloaded CSC arrays
+  * K: rigid-body translations and rotations in the null space, symmetry of the bilinear form, assembled ≡ matrix-free
+  * patch test: a linear displacement field gives zero interior nodal forces, per-element energies V·W(ε) exactly,
+    Σeₑ = Vol·W(ε), constant von Mises stress  (with SIMP densities: scaled by E(ρₑ))
+  * solve: convergence, Σeₑ = ½uᵀKu = ½fᵀu, compliance = fᵀu, prescribed DOFs zero, and — where a frozen value exists —
+    energy / iteration count against tests/golden/fullsize_c3.json
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def structured_counts(dims):
+    nx, ny, nz = dims
+    nn = (nx + 1) * (ny + 1) * (nz + 1)
+    ne = 6 * nx * ny * nz
+    edges = (nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz       # axis edges
+             + nx * ny * (nz + 1) + nx * nz * (ny + 1) + ny * nz * (nx + 1)                       # one diagonal per cube face
+             + nx * ny * nz)                                                                      # the body diagonal c2–c8
+    return nn, ne, 9 * (nn + 2 * edges)
+
+
+def first_touch_node_dofs(cells, nn):
+    """oracle/fea_oracle.py:first_touch_dofs without the (ne × 12) cell_dofs array (1 GB at 10M tets)."""
+    flat = (cells - 1).reshape(-1)
+    _, first_pos = np.unique(flat, return_index=True)
+    order = np.sort(first_pos)
+    nfd = np.zeros(nn, dtype=np.int64)
+    nfd[flat[order]] = 3 * np.arange(order.size, dtype=np.int64) + 1
+    return nfd
+
+
+def hooke_energy_density(G, lam, mu):
+    eps = 0.5 * (G + G.T)
+    tr = np.trace(eps)
+    return 0.5 * (lam * tr * tr + 2.0 * mu * np.sum(eps * eps)), lam * tr * np.eye(3) + 2.0 * mu * eps
+
+
+def run_properties(pkg, ctx, dims, simp=False, golden=None, check_pattern=True, tol_solve=1e-8, itmax=40000, log=None):
+    say = log or (lambda *a: None)
+    nx, ny, nz = dims
+    L = (60.0, 20.0, 4.0)
+    pts, cells = pkg.meshgen.cantilever(*dims)
+    nn, ne, nnz_expected = structured_counts(dims)
+    assert pts.shape[0] == nn and cells.shape[0] == ne
+    out = {}
+
+    # ---- setup_problem -------------------------------------------------------------------------------------------
+    ctx.set_mesh(pts, cells)
+    ndofs = ctx.build_dofs()
+    nnz = ctx.build_pattern()
+    assert ndofs == 3 * nn and nnz == nnz_expected, (ndofs, nnz, nnz_expected)
+    nfd = ctx.node_dofs()
+    assert np.array_equal(nfd, first_touch_node_dofs(cells, nn)), "DOF map differs from the first-touch restatement"
+    say("dof map ok")
+    if check_pattern:
+        colptr, rowval = ctx.pattern()
+        assert colptr[0] == 1 and colptr[-1] == nnz + 1 and np.all(np.diff(colptr) > 0)
+        col_of = np.repeat(np.arange(1, ndofs + 1, dtype=np.int64), np.diff(colptr))
+        # rows ascending inside every column: the flattened key col·n + row must increase strictly
+        key = col_of * np.int64(ndofs + 1) + rowval
+        assert np.all(np.diff(key) > 0), "row indices are not sorted / unique per column"
+        # structural symmetry: the transposed key set is the same set
+        key_t = np.sort(rowval * np.int64(ndofs + 1) + col_of)
+        assert np.array_equal(key, key_t), "pattern is not structurally symmetric"
+        # every DOF sees its own node's three DOFs (diagonal blocks present)
+        assert np.all(np.isin(np.arange(1, ndofs + 1) * np.int64(ndofs + 1) + np.arange(1, ndofs + 1), key, assume_unique=True))
+        del colptr, rowval, col_of, key, key_t
+        say("pattern ok")
+
+    # ---- material + K ---------------------------------------------------------------------------------------------
+    E0, nu, Emin, p = 1.0, 0.3, 1e-8, 3.0
+    lam, mu = pkg.create_material_model(E0, nu)
+    rho = pkg.meshgen.simp_like_density(ne) if simp else None
+    Ee = (Emin + (E0 - Emin) * rho ** p) if simp else np.ones(1)
+    if simp:
+        ctx.assemble_simp(E0, nu, Emin, p, rho)
+    else:
+        ctx.assemble_lame(lam, mu)
+    diag = ctx.diagonal()
+    dmax = float(np.abs(diag).max())
+    assert np.all(diag > 0.0)
+    X = np.empty((nn, 3)); X[(nfd - 1) // 3] = pts                    # coordinates in dof-node order
+    rng = np.random.default_rng(2026)
+
+    def vec(field):                                                   # (nn,3) nodal field in dof-node order -> dof vector
+        return np.ascontiguousarray(field.reshape(-1))
+
+    # rigid-body modes: three translations, three rotations about the box centre
+    c = np.array(L) / 2.0
+    for k in range(3):
+        t = np.zeros((nn, 3)); t[:, k] = 1.0
+        assert np.abs(ctx.spmv(vec(t))).max() <= 1e-12 * dmax
+        w = np.zeros(3); w[k] = 1.0
+        r = np.cross(np.broadcast_to(w, X.shape), X - c)
+        assert np.abs(ctx.spmv(vec(r))).max() <= 1e-12 * dmax * np.abs(r).max()
+    say("rigid body modes ok")
+    # symmetry of the bilinear form and assembled ≡ matrix-free
+    x = rng.standard_normal(ndofs); y = rng.standard_normal(ndofs)
+    Kx = ctx.spmv(x); Ky = ctx.spmv(y)
+    assert abs(y @ Kx - x @ Ky) <= 1e-12 * np.linalg.norm(y) * np.linalg.norm(Kx)
+    Kx_mf = ctx.spmv(x, matrix_free=True)
+    assert np.abs(Kx - Kx_mf).max() <= 1e-12 * dmax * np.abs(x).max()
+    out["spmv_checksum"] = float(np.abs(Kx).sum())
+    del Ky, Kx_mf, y
+    say("symmetry / matrix-free ok")
+
+    # ---- patch test: u = G X -----------------------------------------------------------------------------------------
+    G = np.array([[1.0e-3, 2.0e-4, -3.0e-4], [-1.0e-4, 5.0e-4, 4.0e-4], [2.5e-4, -2.0e-4, -7.0e-4]])
+    ulin = X @ G.T
+    W, sig = hooke_energy_density(G, lam, mu)
+    fint = ctx.spmv(vec(ulin)).reshape(nn, 3)
+    interior = np.all((X > 1e-9) & (X < np.array(L) - 1e-9), axis=1)
+    if not simp:                                                      # with varying E the interior forces do not cancel
+        assert interior.sum() == (nx - 1) * (ny - 1) * (nz - 1)
+        assert np.abs(fint[interior]).max() <= 1e-11 * dmax * np.abs(ulin).max()
+    ctx.set_solution(vec(ulin))
+    e_tot, _, ee = ctx.energy(per_element=True)
+    vol_e = L[0] * L[1] * L[2] / ne
+    ee_expected = Ee * (W * vol_e)
+    assert np.abs(ee - ee_expected).max() <= 1e-11 * np.abs(ee_expected).max()
+    assert abs(e_tot - ee.sum()) <= 1e-11 * e_tot
+    assert abs(e_tot - float(np.sum(Ee) if simp else ne) * W * vol_e) <= 1e-11 * e_tot
+    s = sig - np.trace(sig) / 3.0 * np.eye(3)
+    vm_unit = np.sqrt(1.5 * np.sum(s * s))
+    _, vm, vmax, varg = ctx.stresses(False, True)
+    assert np.abs(vm - Ee * vm_unit).max() <= 1e-11 * vm_unit
+    assert 1 <= varg <= ne and abs(vmax - vm.max()) == 0.0 and vm[varg - 1] == vmax and not np.any(vm[:varg - 1] == vmax)
+    del ee, vm, fint
+    say("patch test ok")
+
+    # ---- loads, Dirichlet, solve -------------------------------------------------------------------------------------
+    fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0)
+    load = pkg.meshgen.nodes_at_plane(pts, 0, L[0])
+    assert fixed.size == load.size == (ny + 1) * (nz + 1)
+    ctx.add_nodal_force(load, [0.0, 0.0, -1.0])
+    f = ctx.rhs()
+    assert abs(f.sum() + 1.0) <= 1e-12 and np.count_nonzero(f) == load.size
+    pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
+    m = ctx.apply_dirichlet(pres)
+    assert abs(m - np.abs(diag).mean()) <= 1e-12 * m                  # Ferrite apply!: mean(abs(diag K)) of the incoming K
+    d2 = ctx.diagonal()
+    assert np.all(d2[pres - 1] == m)
+    free = np.ones(ndofs, dtype=bool); free[pres - 1] = False
+    assert np.array_equal(d2[free], diag[free])
+    st = ctx.solve_pcg(tol_solve, tol_solve, itmax)
+    assert st["converged"] == 1 and st["breakdown"] == 0, st
+    u = ctx.solution()
+    assert np.all(np.isfinite(u)) and np.all(u[pres - 1] == 0.0)
+    e, cmp_, _ = ctx.energy()
+    fu = float(f @ u)
+    assert abs(cmp_ - fu) <= 1e-12 * abs(fu)
+    assert abs(e - 0.5 * fu) <= 1e-6 * e                              # ½uᵀKu = ½fᵀu up to the solver residual
+    assert abs(ctx.energy_assembled() - e) <= 1e-9 * e               # the reference's literal 0.5*dot(u,K*u) with the constrained K
+    Ku = ctx.spmv(u)
+    assert np.linalg.norm(Ku - f) <= 1e-4 * np.linalg.norm(f)
+    assert u.reshape(nn, 3)[:, 2].min() < 0.0                         # the beam bends down
+    out.update(niter=int(st["niter"]), energy=float(e), compliance=float(cmp_), mean_diag=float(m), max_abs_u=float(np.abs(u).max()))
+    if golden is not None:
+        assert abs(e - golden["energy"]) <= 2e-7 * golden["energy"], (e, golden["energy"])
+        assert abs(cmp_ - golden["compliance"]) <= 2e-7 * golden["compliance"]
+        assert abs(st["niter"] - golden["niter"]) <= max(3, golden["niter"] // 50), (st["niter"], golden["niter"])
+        if "mean_diag" in golden:
+            assert abs(m - golden["mean_diag"]) <= 1e-12 * m
+    # matrix-free solve reaches the same answer
+    st_mf = ctx.solve_pcg(tol_solve, tol_solve, itmax, matrix_free=True)
+    e_mf, _, _ = ctx.energy()
+    assert st_mf["converged"] == 1 and abs(e_mf - e) <= 1e-7 * e and abs(st_mf["niter"] - st["niter"]) <= max(3, st["niter"] // 50)
+    say("solve ok", out)
+    return out
