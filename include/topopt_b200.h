@@ -35,6 +35,10 @@ typedef struct toe_ctx toe_ctx;
 #define TOE_ASM_GATHER  2   /* one thread per 3x3 block of K, loops its contributing elements in ascending
                                cell order (the reference's accumulation order, Ferrite assemble!): no atomics,
                                deterministic, coalesced writes */
+#define TOE_ASM_ROWS    3   /* Tet4: a thread group per node row stages the geometry of the row's cells once in shared
+                               memory, then one thread per block of the row accumulates in ascending cell order
+                               (≈2.3x fewer FP64 operations than GATHER; same determinism and exact symmetry; values
+                               differ from GATHER in the last bits only).  Falls back to GATHER for Hex8 / very wide rows */
 
 /* toe_solve_pcg flags */
 #define TOE_PCG_MATRIX_FREE   1   /* element-by-element operator, K is not read (nor needed) */

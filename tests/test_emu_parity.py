@@ -52,3 +52,14 @@ for _n in ["test_dofs_and_pattern_bit_exact", "test_dofs_permuted_cells_and_unre
 for _n in ["test_solve_c1_tet_beam", "test_pcg_krylov_semantics_and_iteration_count", "test_solve_c2_hex_simp", "test_runtests_recipe_linear_beam",
            "test_runtests_recipe_simp_beam", "test_gravity_cantilever_known_answer"]:
     _adopt(_n, slow=True)
+
+
+def test_rows_assembly_variant(ctx, pkg, fo, golden_c1):
+    import rows_variant_checks as rc
+    rc.check_rows_variant(pkg, fo, ctx, golden_c1)
+    for g in ("32", "64"):                            # the wider thread groups on the structured mesh as well
+        os.environ["TOE_ASM_ROWS_G"] = g
+        try:
+            rc.check_rows_variant(pkg, fo, ctx, golden_c1)
+        finally:
+            del os.environ["TOE_ASM_ROWS_G"]

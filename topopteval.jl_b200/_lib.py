@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtopopt_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
-ASM_AUTO, ASM_ATOMIC, ASM_GATHER = 0, 1, 2
+ASM_AUTO, ASM_ATOMIC, ASM_GATHER, ASM_ROWS = 0, 1, 2, 3
 PCG_MATRIX_FREE, PCG_NO_GRAPH = 1, 2
 
 

@@ -10,6 +10,7 @@
 // fully coalesced 8-byte stream.
 #include "element.cuh"
 #include <climits>
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------------------
 // vectors / scratch
@@ -252,6 +253,128 @@ __global__ void __launch_bounds__(128) k_asm_diag(const int* __restrict__ inc_pt
     for (int k = 0; k < 9; k++) val[(size_t)k * nnzb + s] = acc[k];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// assembly, variant ROWS (Tet4): a group of G threads owns one node row of K.
+//   pass 1  the group evaluates the geometry of the row's cells ONCE (gradients, w·λ, w·μ; ASM_CH cells per pass) into
+//           shared memory — the gather variant re-derives it for every block, 4x per (row, cell);
+//   pass 2  thread `lane` owns block slot blk_ptr[row]+lane and walks its (e,a,b) list (diagonal block: the row's own
+//           incidence list) in ascending cell order, reading g_a, g_b, wλ, wμ from shared memory:
+//              B += wλ g_a⊗g_b + wμ g_b⊗g_a + wμ (g_a·g_b) I        (9 DMUL + 21 DFMA + 2 DADD per contribution)
+// Products g_a[c]·g_b[d] are shared by block (a,b) and its transpose and the accumulation order is the cell order, so K
+// stays bitwise symmetric and bit-reproducible.  ≈2.3x fewer FP64 operations per element than GATHER.
+// ---------------------------------------------------------------------------------------------------------
+static const int ASM_ROWS_THREADS = 128;
+static const int ASM_CH = 32;                 // cells of a row staged per pass
+static const int ASM_GEO = 14;                // doubles per staged cell: g[4][3], w·λ, w·μ
+
+__device__ __forceinline__ void block_acc(const double* __restrict__ ga, const double* __restrict__ gb, double wl, double wm, double acc[9]) {
+    double p[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) p[c][d] = ga[c] * gb[d];
+    const double dot = (p[0][0] + p[1][1]) + p[2][2];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            double v = fma(wl, p[c][d], acc[3 * c + d]);
+            acc[3 * c + d] = fma(wm, p[d][c], v);
+        }
+#pragma unroll
+    for (int c = 0; c < 3; c++) acc[4 * c] = fma(wm, dot, acc[4 * c]);
+}
+
+template <int G>
+__global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+                                                                   const int* __restrict__ blk_ptr, const int* __restrict__ blk_col,
+                                                                   const int* __restrict__ ctr_ptr, const int* __restrict__ ctr,
+                                                                   const int* __restrict__ cq, const double* __restrict__ xq, Material mat,
+                                                                   double* __restrict__ val, i64 ldv, int nq, int* err) {
+    constexpr int ROWS = ASM_ROWS_THREADS / G;
+    __shared__ double geo[ROWS][ASM_CH][ASM_GEO];
+    __shared__ int cell[ROWS][ASM_CH];             // e*4 + (corner of the row node in e)
+    __shared__ double dpart[ASM_ROWS_THREADS][6];  // per-thread partial of the row's diagonal block (upper triangle)
+    __shared__ int s_maxcells;
+    const int rl = threadIdx.x / G, lane = threadIdx.x - rl * G;
+    const int row = blockIdx.x * ROWS + rl;
+    const bool live = row < nq;
+    int i_lo = 0, i_hi = 0, s = -1, col = -1, ci = 0, chi = 0;
+    if (live) {
+        i_lo = __ldg(&inc_ptr[row]); i_hi = __ldg(&inc_ptr[row + 1]);
+        const int b0 = __ldg(&blk_ptr[row]), b1 = __ldg(&blk_ptr[row + 1]);
+        if (lane < b1 - b0) { s = b0 + lane; col = __ldg(&blk_col[s]); ci = __ldg(&ctr_ptr[s]); chi = __ldg(&ctr_ptr[s + 1]); }
+    }
+    if (threadIdx.x == 0) s_maxcells = 0;
+    __syncthreads();
+    if (live && lane == 0) atomicMax(&s_maxcells, i_hi - i_lo);
+    __syncthreads();
+    const int npass = (s_maxcells + ASM_CH - 1) / ASM_CH;       // CTA-uniform: the barriers below are reached by every thread
+    const bool is_diag = (s >= 0 && col == row);
+    double acc[9], dacc[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { acc[k] = 0.0; dacc[k] = 0.0; }
+    for (int pass = 0; pass < npass; pass++) {
+        const int k0 = i_lo + pass * ASM_CH;
+        int cnt = live ? i_hi - k0 : 0;
+        cnt = cnt < 0 ? 0 : (cnt > ASM_CH ? ASM_CH : cnt);
+        for (int k = lane; k < cnt; k += G) {
+            const int ea = __ldg(&inc[k0 + k]);
+            const int e = ea >> 2;
+            double lam, mu; material_at(mat, e, lam, mu);
+            int q[4]; double X[4][3], g[4][3];
+            tet_load(cq, xq, e, q, X);
+            const double det = tet_grads(X, g);
+            if (!(det > 0.0)) atomicMin(err + 1, e);
+            const double w = det * (1.0 / 6.0);
+            double* o = geo[rl][k];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int i = 0; i < 3; i++) o[3 * a + i] = g[a][i];
+            o[12] = w * lam; o[13] = w * mu;
+            cell[rl][k] = ea;
+            // the diagonal block has a contribution from every cell of the row (4x the work of an off-diagonal block): it is
+            // spread over the group here — each thread adds its cells (ascending), the partials are summed in lane order below
+            const double* ga = o + 3 * (ea & 3);
+            block_acc(ga, ga, o[12], o[13], dacc);
+        }
+        __syncthreads();
+        if (s >= 0 && cnt > 0) {
+            if (!is_diag) {
+                const int e_last = cell[rl][cnt - 1] >> 2;
+                int k = 0;
+                while (ci < chi) {
+                    int e, a, b; ctr_unpack<4>(__ldg(&ctr[ci]), e, a, b);
+                    if (e > e_last) break;                                   // belongs to a later pass
+                    while (k < cnt && (cell[rl][k] >> 2) != e) k++;
+                    if (k >= cnt) { atomicExch(err + 2, 1); ci = chi; break; }   // lists out of step (cannot happen with lists built by mesh.cu)
+                    const double* o = geo[rl][k];
+                    block_acc(o + 3 * a, o + 3 * b, o[12], o[13], acc);
+                    ci++;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    dpart[threadIdx.x][0] = dacc[0]; dpart[threadIdx.x][1] = dacc[1]; dpart[threadIdx.x][2] = dacc[2];
+    dpart[threadIdx.x][3] = dacc[4]; dpart[threadIdx.x][4] = dacc[5]; dpart[threadIdx.x][5] = dacc[8];
+    __syncthreads();
+    if (is_diag) {
+        double d[6] = {0, 0, 0, 0, 0, 0};
+        for (int l = 0; l < G; l++) {
+            const double* pp = dpart[rl * G + l];
+#pragma unroll
+            for (int k = 0; k < 6; k++) d[k] += pp[k];
+        }
+        acc[0] = d[0]; acc[1] = d[1]; acc[2] = d[2]; acc[3] = d[1]; acc[4] = d[3]; acc[5] = d[4]; acc[6] = d[2]; acc[7] = d[4]; acc[8] = d[5];
+    }
+    if (s >= 0) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) val[(size_t)k * ldv + s] = acc[k];
+    }
+}
+
 __global__ void k_simp_lame(Material mat, double* __restrict__ lam_e, double* __restrict__ mu_e, int ne) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ne) return;
@@ -259,10 +382,11 @@ __global__ void k_simp_lame(Material mat, double* __restrict__ lam_e, double* __
     lam_e[e] = lam; mu_e[e] = mu;
 }
 
-static int check_detj(toe_ctx* ctx, const char* who) {
+static int check_detj(toe_ctx* ctx, const char* who, int* aux_flag = nullptr) {
     int h[4];
     CU(cudaMemcpyAsync(h, ctx->errflag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (aux_flag) *aux_flag = h[2];
     if (h[1] != INT_MAX) {
         int bad = h[1];
         int reset = INT_MAX;
@@ -283,8 +407,10 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
     if (ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "assemble: no material set");
     TRY(ensure_vectors(ctx));
     if (variant == TOE_ASM_AUTO) variant = TOE_ASM_GATHER;
-    if (variant != TOE_ASM_ATOMIC && variant != TOE_ASM_GATHER) return toe_fail(ctx, TOE_ERR_ARG, "unknown assembly variant %d", variant);
-    if (variant == TOE_ASM_GATHER) TRY(mesh_build_contrib(ctx));      // one-off per mesh, outside the timed stage
+    if (variant != TOE_ASM_ATOMIC && variant != TOE_ASM_GATHER && variant != TOE_ASM_ROWS) return toe_fail(ctx, TOE_ERR_ARG, "unknown assembly variant %d", variant);
+    // ROWS is written for Tet4 and rows of at most 64 blocks; everything else takes the GATHER kernels
+    if (variant == TOE_ASM_ROWS && (ctx->npc != 4 || ctx->max_deg > 64)) variant = TOE_ASM_GATHER;
+    if (variant != TOE_ASM_ATOMIC) TRY(mesh_build_contrib(ctx));      // one-off per mesh, outside the timed stage
     size_t n = 3 * (size_t)ctx->nq;
     i64 nnzb = ctx->nnzb, ldv = ctx->ldv;
     if (ctx->val.n < 9 * (size_t)ldv + 16) {
@@ -293,9 +419,9 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
     }
     TRY(reset_detj_flag(ctx));
     Material amat = ctx->mat;
-    if (variant == TOE_ASM_GATHER && ctx->mat.mode == MAT_SIMP) { CU(ctx->lamw.alloc(ctx->ne)); CU(ctx->muw.alloc(ctx->ne)); }
+    if (variant != TOE_ASM_ATOMIC && ctx->mat.mode == MAT_SIMP) { CU(ctx->lamw.alloc(ctx->ne)); CU(ctx->muw.alloc(ctx->ne)); }
     StageTimer T(ctx, &ctx->tm.assemble);
-    if (variant == TOE_ASM_GATHER && ctx->mat.mode == MAT_SIMP) {
+    if (variant != TOE_ASM_ATOMIC && ctx->mat.mode == MAT_SIMP) {
         // the gather kernels visit a cell once per block it contributes to: evaluate E(ρ)=Emin+(E0-Emin)ρ^p once per cell instead
         LAUNCH(ctx, k_simp_lame, div_up(ctx->ne, 256), 256, 0, ctx->mat, ctx->lamw.p, ctx->muw.p, (int)ctx->ne);
         amat.mode = MAT_PERCELL; amat.lam_e = ctx->lamw.p; amat.mu_e = ctx->muw.p;
@@ -315,6 +441,16 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
         else
             LAUNCH(ctx, k_asm_atomic_hex, div_up((i64)ne * 8, 64), 64, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat,
                    (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, ctx->val.p, ldv, ne, ctx->errflag.p);
+    } else if (variant == TOE_ASM_ROWS) {
+        CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
+#define ROWS_ARGS (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const int*)ctx->ctr_ptr.p, \
+        (const int*)ctx->ctr.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p, amat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p
+        int gmin = 0;                                         // TOE_ASM_ROWS_G=32|64 forces a wider group (tests)
+        if (const char* eg = getenv("TOE_ASM_ROWS_G")) gmin = atoi(eg);
+        if (ctx->max_deg <= 16 && gmin <= 16)      LAUNCH(ctx, k_asm_rows_tet<16>, div_up(ctx->nq, ASM_ROWS_THREADS / 16), ASM_ROWS_THREADS, 0, ROWS_ARGS);
+        else if (ctx->max_deg <= 32 && gmin <= 32) LAUNCH(ctx, k_asm_rows_tet<32>, div_up(ctx->nq, ASM_ROWS_THREADS / 32), ASM_ROWS_THREADS, 0, ROWS_ARGS);
+        else                         LAUNCH(ctx, k_asm_rows_tet<64>, div_up(ctx->nq, ASM_ROWS_THREADS / 64), ASM_ROWS_THREADS, 0, ROWS_ARGS);
+#undef ROWS_ARGS
     } else {
         if (ctx->npc == 4) {
             LAUNCH(ctx, k_asm_offdiag<4>, div_up(nnzb, 128), 128, 0, (const int*)ctx->ctr_ptr.p, (const int*)ctx->ctr.p,
@@ -329,7 +465,9 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
         }
     }
     TRY(T.finish());
-    TRY(check_detj(ctx, "assemble_stiffness_matrix"));
+    int lists_bad = 0;
+    TRY(check_detj(ctx, "assemble_stiffness_matrix", variant == TOE_ASM_ROWS ? &lists_bad : nullptr));
+    if (lists_bad) return toe_fail(ctx, TOE_ERR_STATE, "assemble (ROWS): incidence and contribution lists are out of step (internal error)");
     ctx->have_K = true; ctx->have_diag = false; ctx->have_solution = false;
     ctx->op_generation++;
     return TOE_OK;
