@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {"C3_1M": (120, 50, 28), "C4_10M": (260, 110, 58), "C5_60M": (480, 200, 104), "tiny": (24, 8, 4), "200k": (96, 32, 12)}
+WORKLOADS = {"C3_1M": (120, 50, 28), "C4_10M": (260, 110, 58), "C5_60M": (480, 200, 104), "tiny": (24, 8, 4), "toy": (8, 3, 2), "200k": (96, 32, 12)}
 CPU_SAMPLE = tuple(int(x) for x in os.environ.get("TOE_BENCH_CPU_SAMPLE", "60,20,8").split(","))   # 57 600 tets: ≈8 s (here) / ≈3 s (GPU box) of single-core CPU work per step
 TOL = 1e-8
 ITMAX = 40000                     # 13 689 iterations are needed at 10M tets; a stagnating solve must end quickly, not after 100 000
@@ -214,35 +214,64 @@ def run_b200(args, pkg):
     pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
     ne_total = cells.shape[0]
 
+    def any_rank(flag):
+        if dist is None:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item())
+
     # ---- device-resident arm: W warm-up steps, then exactly K timed steps -------------------------------------
-    for w in range(args.warmup):
-        stw, _, _ = step()
-        if not stw["converged"]:
-            print("bench.py: warm-up step %d did not converge (niter=%d, breakdown=%d)" % (w, stw["niter"], stw["breakdown"]), file=sys.stderr, flush=True)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    launches0 = ctx.timings()["kernel_launches"]
-    sampler.start()
-    ctx.timer_start()
-    t0 = time.perf_counter()
-    stage_acc = {"assemble": 0.0, "solve": 0.0, "spmv": 0.0, "energy": 0.0, "loads": 0.0, "dirichlet": 0.0}
-    st = e = c = None
-    restarts = 0
-    for _ in range(args.steps):
-        st, e, c = step()
-        restarts += int(st.get("restarts", 0))
-        if not st["converged"] or st["breakdown"]:
-            raise SystemExit("bench.py: a timed step did not converge (niter=%d, breakdown=%d, rel_res=%g) — no number reported" % (st["niter"], st["breakdown"], st["rel_res_l2"]))
-        tm = ctx.timings()
-        stage_acc["assemble"] += tm["assemble"]; stage_acc["solve"] += tm["solve"]; stage_acc["energy"] += tm["energy"]
-        stage_acc["loads"] += tm["loads"]; stage_acc["dirichlet"] += tm["dirichlet"]; stage_acc["spmv"] += st["spmv_seconds"]
-    dev_s = ctx.timer_stop()
-    barrier()
-    wall_s = time.perf_counter() - t0
-    clocks = sampler.stop()
-    launches = ctx.timings()["kernel_launches"] - launches0
-    dev_s = max_over_ranks(dev_s)
-    wall_s = max_over_ranks(wall_s)
+    # Partitioned runs only: a set-up whose solves break down (open item 2) is discarded — mesh re-partitioned,
+    # warm-ups and timed steps repeated — at most twice; `measurement_attempts` in the JSON line says how often that happened.
+    # A timed region is only ever reported if every one of its K steps converged.
+    def measure():
+        bad = False
+        for w in range(args.warmup):
+            stw, _, _ = step()
+            if not stw["converged"]:
+                bad = True
+                print("bench.py: warm-up step %d did not converge (niter=%d, breakdown=%d)" % (w, stw["niter"], stw["breakdown"]), file=sys.stderr, flush=True)
+        if any_rank(bad):
+            return None
+        sampler = ClockSampler(local_rank)
+        barrier()
+        launches0 = ctx.timings()["kernel_launches"]
+        sampler.start()
+        ctx.timer_start()
+        t0 = time.perf_counter()
+        acc = {"assemble": 0.0, "solve": 0.0, "spmv": 0.0, "energy": 0.0, "loads": 0.0, "dirichlet": 0.0}
+        st = e = c = None
+        restarts = 0
+        for _ in range(args.steps):
+            st, e, c = step()
+            restarts += int(st.get("restarts", 0))
+            if not st["converged"] or st["breakdown"]:
+                bad = True
+            tm = ctx.timings()
+            acc["assemble"] += tm["assemble"]; acc["solve"] += tm["solve"]; acc["energy"] += tm["energy"]
+            acc["loads"] += tm["loads"]; acc["dirichlet"] += tm["dirichlet"]; acc["spmv"] += st["spmv_seconds"]
+        dev_s = ctx.timer_stop()
+        barrier()
+        wall_s = time.perf_counter() - t0
+        clocks = sampler.stop()
+        launches = ctx.timings()["kernel_launches"] - launches0
+        if any_rank(bad):
+            print("bench.py: a timed step did not converge (niter=%d, breakdown=%d, rel_res=%g)" % (st["niter"], st["breakdown"], st["rel_res_l2"]), file=sys.stderr, flush=True)
+            return None
+        return dict(st=st, e=e, c=c, restarts=restarts, stage_acc=acc, dev_s=max_over_ranks(dev_s), wall_s=max_over_ranks(wall_s), clocks=clocks, launches=launches)
+
+    attempts = 0
+    m = None
+    while m is None:
+        attempts += 1
+        m = measure()
+        if m is None:
+            if world == 1 or attempts >= 3:
+                raise SystemExit("bench.py: PCG did not converge in the timed region (attempt %d) — no number reported" % attempts)
+            setup()
+    st, e, c, restarts, stage_acc = m["st"], m["e"], m["c"], m["restarts"], m["stage_acc"]
+    dev_s, wall_s, clocks, launches = m["dev_s"], m["wall_s"], m["clocks"], m["launches"]
     value = ne_total * args.steps / dev_s
 
     # dominant kernel (SpMV inside PCG): live CUDA-event timing of back-to-back launches on the library's stream
@@ -263,8 +292,13 @@ def run_b200(args, pkg):
     e2e_steps = min(args.steps, 3)                        # bounded: the e2e arm repeats the full path incl. setup
     barrier()
     t0 = time.perf_counter()
+    e2e_retries = 0
     for _ in range(e2e_steps):
-        st2, e2, c2, u = e2e_step()
+        for attempt in range(3):                          # partitioned runs: a step whose solve broke down is repeated INSIDE the timed region
+            st2, e2, c2, u = e2e_step()
+            if not any_rank(not st2["converged"]) or world == 1:
+                break
+            e2e_retries += 1
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     # the end-to-end arm must have done the same work and reached the same answer as the device-resident arm
@@ -276,8 +310,6 @@ def run_b200(args, pkg):
     h2d = pts.nbytes + cells.nbytes + load.nbytes + pres.nbytes
     d2h = u.nbytes + 2 * 8 + 128
 
-    if not st["converged"] or st["breakdown"]:
-        raise SystemExit("bench.py: PCG did not converge (niter=%d, breakdown=%d, rel_res=%g) — no number reported" % (st["niter"], st["breakdown"], st["rel_res_l2"]))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -288,13 +320,13 @@ def run_b200(args, pkg):
                        "operator": "matrix-free EbE" if mf else "assembled block-CSR", "parallelism": "dd%d" % world,
                        "exchange": ctx.comm_info()["transport"],
                        "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (ctx.nnz * 8 / 1e9),
-                       "wall_ms_per_step": 1e3 * wall_s / args.steps},
+                       "wall_ms_per_step": 1e3 * wall_s / args.steps, "measurement_attempts": attempts},
             "clocks": clocks,
             "e2e": {"value": None if e2e_invalid else ne_total * e2e_steps / e2e_s, "invalid": e2e_invalid, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pcg_iterations": int(st2["niter"]), "energy": e2,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "repeated_steps": e2e_retries, "pcg_iterations": int(st2["niter"]), "energy": e2,
                     "path": "host mesh (pinned) -> toe_set_mesh -> build_dofs -> build_pattern -> assemble -> loads -> apply! -> PCG -> energy -> u to host"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_ebe_gather" if mf else "k_spmv_bsr_pipe", "bound": "hbm", "achieved": spmv_bytes / spmv_s / 1e9, "peak": peaks["hbm_gbs"],
+            "roofline": {"kernel": "k_ebe_tile+k_ebe_nodes" if mf else "k_spmv_bsr_pipe", "bound": "hbm", "achieved": spmv_bytes / spmv_s / 1e9, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": spmv_bytes / spmv_s / 1e9 / peaks["hbm_gbs"], "traffic": profile_traffic(mf), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": spmv_bytes, "launch_seconds": spmv_s,
                          "share_of_step": stage_acc["spmv"] / dev_s},

@@ -1,0 +1,42 @@
+"""bench.py's B200 arm driven end to end on the EMULATED build (tests/cuda_emu, test infrastructure): the toy workload,
+torch.cuda calls stubbed.  Checks the script's control flow and the JSON contract — never a measurement."""
+import io
+import json
+import os
+import sys
+import types
+from contextlib import redirect_stdout
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import emu_support  # noqa: E402
+
+
+@pytest.mark.parametrize("mf", [False, True])
+def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
+    import torch
+    pkg, lib = emu_support.load_emu()
+    import bench
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=mf, no_cpu_baseline=True)
+    buf = io.StringIO()
+    with emu_support.emulated(pkg, lib), redirect_stdout(buf):
+        bench.run_b200(args, pkg)
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "clocks", "e2e", "gpu_launches", "roofline", "stages"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["unit"] == "elements/s" and d["dtype"] == "f64"
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+    assert "workload" in d["config"] and d["config"]["measurement_attempts"] == 1
+    e2e = d["e2e"]
+    assert e2e["value"] > 0 and e2e["invalid"] is None and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and e2e["repeated_steps"] == 0
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
+    assert d["stages"]["pcg_converged"] and d["stages"]["pcg_iterations"] > 0 and d["stages"]["energy"] > 0
