@@ -49,7 +49,8 @@ emu_switch:
 
 namespace {
 
-struct Fiber { void* sp = nullptr; char* stack = nullptr; bool done = true; };
+struct PendingCopy { void* dst; const void* src; unsigned bytes; };
+struct Fiber { void* sp = nullptr; char* stack = nullptr; bool done = true; std::vector<PendingCopy> pending; };
 
 struct Warp { unsigned long long slot[2][32]; unsigned arrived; unsigned long long gen; unsigned live; };
 
@@ -99,6 +100,8 @@ void fiber_entry() {
     Rank& r = *g_rank;
     (*r.body)();
     Fiber& f = r.fibers[r.cur];
+    for (auto& c : f.pending) memcpy(c.dst, c.src, c.bytes);     // the hardware completes outstanding copies eventually
+    f.pending.clear();
     f.done = true;
     r.progress++;
     emu_switch(&f.sp, r.sched_sp);
@@ -120,6 +123,7 @@ void fiber_prepare(Rank& r, int t) {
     for (int k = 0; k < 6; k++) *--sp = nullptr;   // rbp rbx r12 r13 r14 r15
     f.sp = (void*)sp;
     f.done = false;
+    f.pending.clear();
 }
 
 void block_state_init(BlockState& bs, unsigned T) {
@@ -209,6 +213,20 @@ void launch(unsigned grid, unsigned block, size_t smem, std::function<void()> bo
     run_grid(r, grid, block, smem, body);
 }
 void* dyn_smem() { return g_rank->dyn; }
+void cp_async(void* dst, const void* src, unsigned bytes) {
+    if ((bytes != 4 && bytes != 8 && bytes != 16) || ((size_t)dst % bytes) || ((size_t)src % bytes)) {
+        fprintf(stderr, "cuda_emu: illegal cp.async (%u bytes, dst %p, src %p)\n", bytes, dst, src);
+        g_rank->last_error = 716;
+    }
+    Rank& r = *g_rank;
+    r.fibers[r.cur].pending.push_back(PendingCopy{dst, src, bytes});
+}
+void cp_async_wait_all() {
+    Rank& r = *g_rank;
+    Fiber& f = r.fibers[r.cur];
+    for (auto& c : f.pending) memcpy(c.dst, c.src, c.bytes);
+    f.pending.clear();
+}
 void next_launch_coresident() { rank_state().next_coresident = true; }
 static thread_local unsigned g_jitter_state = 12345u;
 void yield() {

@@ -105,6 +105,8 @@ namespace emu {
 void launch(unsigned grid, unsigned block, size_t smem, std::function<void()> body);   // runs (or records, during capture) the grid
 void* dyn_smem();                          // dynamic shared memory of the running block
 void yield();                              // cooperative reschedule (used by spin loops)
+void cp_async(void* dst, const void* src, unsigned bytes);   // cp.async modelled at its LATEST legal completion: performed at the issuing thread's wait
+void cp_async_wait_all();
 void next_launch_coresident();             // the next launch runs all its blocks at once (software grid barrier inside)
 void sync_threads();
 void named_barrier(int id, int count);

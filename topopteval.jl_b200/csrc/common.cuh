@@ -109,7 +109,8 @@ struct toe_ctx {
     bool have_tiles = false;
     int ntiles = 0, tile_elems = 0, tile_max_nodes = 0;
     i64 tile_slots = 0;                                   // Σ local nodes over tiles = rows of the staging array
-    DevBuf<int> tile_off, tile_nodes;                     // [ntiles+1], [tile_slots]: dof-node id of each local node
+    DevBuf<int> tile_off, tile_nodes;                     // [ntiles+1] (each tile's rows padded to a multiple of 8), [tile_slots]: dof-node id of each local node, -1 = padding
+    DevBuf<int> tile_m;                                   // [ntiles]: local nodes of each tile
     DevBuf<unsigned short> tile_lconn, tile_inc, tile_nstart;   // local connectivity, node-sorted ref ids, first ref of each local node
     DevBuf<int> nst_ptr, nst;                             // node -> staging rows (ascending)
     DevBuf<double> tile_stage;                            // 3 doubles per staging row

@@ -16,6 +16,8 @@
 // product are evaluated once per cell instead of once per (cell, corner).
 #include "element.cuh"
 #include <climits>
+#include <cstdlib>
+#include <cstdio>
 
 static const int TILE_REFS = 1024;          // refs (cell corners) per tile
 
@@ -84,15 +86,26 @@ __global__ void __launch_bounds__(256) k_tile_build(const int* __restrict__ cq, 
     if (tid == 0) tile_m[t] = m;
 }
 
-__global__ void k_tile_compact(const int* __restrict__ tile_off, const int* __restrict__ nodes_tmp, const unsigned short* __restrict__ nstart_tmp,
+__global__ void k_tile_pad(const int* __restrict__ tile_m, int* __restrict__ padded, int ntiles) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles) padded[t] = (tile_m[t] + 7) & ~7;       // 8-row granularity: every tile's slice of the metadata arrays is 16-byte aligned
+}
+
+__global__ void k_tile_compact(const int* __restrict__ tile_off, const int* __restrict__ tile_m, const int* __restrict__ nodes_tmp,
+                               const unsigned short* __restrict__ nstart_tmp,
                                int* __restrict__ tile_nodes, unsigned short* __restrict__ tile_nstart, int* __restrict__ cnt, int* max_m) {
     const int t = blockIdx.x;
-    const int off = tile_off[t], m = tile_off[t + 1] - off;
-    for (int j = threadIdx.x; j < m; j += blockDim.x) {
-        int q = nodes_tmp[(size_t)t * TILE_REFS + j];
-        tile_nodes[off + j] = q;
-        tile_nstart[off + j] = nstart_tmp[(size_t)t * TILE_REFS + j];
-        atomicAdd(&cnt[q], 1);
+    const int off = tile_off[t], m = tile_m[t], mp = tile_off[t + 1] - off;
+    for (int j = threadIdx.x; j < mp; j += blockDim.x) {
+        if (j < m) {
+            int q = nodes_tmp[(size_t)t * TILE_REFS + j];
+            tile_nodes[off + j] = q;
+            tile_nstart[off + j] = nstart_tmp[(size_t)t * TILE_REFS + j];
+            atomicAdd(&cnt[q], 1);
+        } else {
+            tile_nodes[off + j] = -1;                       // padding row
+            tile_nstart[off + j] = 0;
+        }
     }
     if (threadIdx.x == 0) atomicMax(max_m, m);
 }
@@ -101,6 +114,7 @@ __global__ void k_nst_fill(const int* __restrict__ tile_nodes, const int* __rest
     i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslots) return;
     int q = tile_nodes[s];
+    if (q < 0) return;
     nst[nst_ptr[q] + atomicAdd(&cursor[q], 1)] = (int)s;
 }
 __global__ void k_nst_sort(const int* __restrict__ nst_ptr, int* __restrict__ nst, int nq) {
@@ -116,22 +130,23 @@ int mesh_build_tiles(toe_ctx* ctx) {
     const int npc = ctx->npc, TE = TILE_REFS / npc;
     const i64 ne = ctx->ne;
     const int ntiles = (int)((ne + TE - 1) / TE), nq = ctx->nq;
-    CU(ctx->tile_off.alloc(ntiles + 1));
-    CU(ctx->tile_lconn.alloc(ne * npc)); CU(ctx->tile_inc.alloc(ne * npc));
+    CU(ctx->tile_off.alloc(ntiles + 1)); CU(ctx->tile_m.alloc(ntiles + 1));
+    CU(ctx->tile_lconn.alloc(ne * npc + 64)); CU(ctx->tile_inc.alloc(ne * npc + 64));      // slack: the pipelined kernel copies in 16-byte units
     DevBuf<int> nodes_tmp; DevBuf<unsigned short> nstart_tmp;
     CU(nodes_tmp.alloc((size_t)ntiles * TILE_REFS)); CU(nstart_tmp.alloc((size_t)ntiles * TILE_REFS));
-    if (npc == 4) LAUNCH(ctx, k_tile_build<4>, ntiles, 256, 0, (const int*)ctx->cq.p, ne, ctx->tile_off.p, nodes_tmp.p, ctx->tile_lconn.p, ctx->tile_inc.p, nstart_tmp.p);
-    else          LAUNCH(ctx, k_tile_build<8>, ntiles, 256, 0, (const int*)ctx->cq.p, ne, ctx->tile_off.p, nodes_tmp.p, ctx->tile_lconn.p, ctx->tile_inc.p, nstart_tmp.p);
+    if (npc == 4) LAUNCH(ctx, k_tile_build<4>, ntiles, 256, 0, (const int*)ctx->cq.p, ne, ctx->tile_m.p, nodes_tmp.p, ctx->tile_lconn.p, ctx->tile_inc.p, nstart_tmp.p);
+    else          LAUNCH(ctx, k_tile_build<8>, ntiles, 256, 0, (const int*)ctx->cq.p, ne, ctx->tile_m.p, nodes_tmp.p, ctx->tile_lconn.p, ctx->tile_inc.p, nstart_tmp.p);
+    LAUNCH(ctx, k_tile_pad, div_up(ntiles, 256), 256, 0, (const int*)ctx->tile_m.p, ctx->tile_off.p, ntiles);
     i64 nslots = 0;
     TRY(scan_exclusive_i32(ctx, ctx->tile_off.p, ctx->tile_off.p, ntiles, &nslots));
-    CU(ctx->tile_nodes.alloc(nslots)); CU(ctx->tile_nstart.alloc(nslots));
+    CU(ctx->tile_nodes.alloc(nslots + 8)); CU(ctx->tile_nstart.alloc(nslots + 8));
     CU(ctx->nst_ptr.alloc(nq + 1)); CU(ctx->nst.alloc(nslots));
     CU(ctx->tile_stage.alloc(3 * (size_t)nslots));
     DevBuf<int> cursor; CU(cursor.alloc(nq + 1));
     CU(cudaMemsetAsync(ctx->nst_ptr.p, 0, (nq + 1) * sizeof(int), ctx->stream));
     CU(cudaMemsetAsync(cursor.p, 0, (nq + 1) * sizeof(int), ctx->stream));
     CU(cudaMemsetAsync(ctx->errflag.p + 3, 0, sizeof(int), ctx->stream));
-    LAUNCH(ctx, k_tile_compact, ntiles, 128, 0, (const int*)ctx->tile_off.p, (const int*)nodes_tmp.p, (const unsigned short*)nstart_tmp.p,
+    LAUNCH(ctx, k_tile_compact, ntiles, 128, 0, (const int*)ctx->tile_off.p, (const int*)ctx->tile_m.p, (const int*)nodes_tmp.p, (const unsigned short*)nstart_tmp.p,
            ctx->tile_nodes.p, ctx->tile_nstart.p, ctx->nst_ptr.p, ctx->errflag.p + 3);
     int max_m = 0;
     CU(cudaMemcpyAsync(&max_m, ctx->errflag.p + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -149,7 +164,7 @@ int mesh_build_tiles(toe_ctx* ctx) {
 // operator
 // ---------------------------------------------------------------------------------------------------------
 template <int NPC, bool MASK>
-__global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restrict__ tile_off, const int* __restrict__ tile_nodes,
+__global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restrict__ tile_off, const int* __restrict__ tile_m, const int* __restrict__ tile_nodes,
                                                               const unsigned short* __restrict__ lconn, const unsigned short* __restrict__ inc_sorted,
                                                               const unsigned short* __restrict__ nstart, const double* __restrict__ xq, Material mat,
                                                               const unsigned char* __restrict__ dflag, const double* __restrict__ x,
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restr
     TOE_DYN_SMEM(double, sm, 16);
     if (done_flag && *done_flag) return;
     const int t = blockIdx.x, tid = threadIdx.x;
-    const int off = __ldg(&tile_off[t]), m = __ldg(&tile_off[t + 1]) - off;
+    const int off = __ldg(&tile_off[t]), m = __ldg(&tile_m[t]);
     const i64 e0 = (i64)t * TE;
     const int nel = (int)min((i64)TE, ne - e0);
     const int nref = nel * NPC;
@@ -265,6 +280,212 @@ __global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// operator, pipelined form (opt-in: TOE_EBE_PIPE=1; Tet4 and Hex8, no column masking)
+//
+// k_ebe_tile spends most of a tile's life waiting: new CTA → tile_off → tile_nodes → x/xq is a chain of three dependent
+// DRAM/L2 latencies before the first FMA (ncu, r1: FP64 pipe 22 %, no dominant stall).  Here a PERSISTENT CTA walks tiles
+// t = blockIdx.x, += gridDim.x with a three-deep software pipeline of asynchronous copies (cp.async → SASS LDGSTS):
+//     iteration i:   wait for {node data of tile i, metadata of tile i+1}            cp.async.wait_all + barrier
+//                    issue  {metadata of tile i+2 (contiguous, 16-byte copies),
+//                            node gather of tile i+1 (8-byte copies, addresses from its metadata in shared memory)}
+//                    compute tile i from shared memory (same arithmetic and summation order as k_ebe_tile → same bits)
+// so every global latency is hidden behind a whole tile of compute.  Metadata slices are 16-byte aligned because every
+// tile's rows are padded to a multiple of 8 (mesh_build_tiles).
+// ---------------------------------------------------------------------------------------------------------
+#ifndef TOE_EMU
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else
+static inline void cp_async_16(void* dst, const void* src) { emu::cp_async(dst, src, 16); }
+static inline void cp_async_8(void* dst, const void* src) { emu::cp_async(dst, src, 8); }
+static inline void cp_async_commit() {}
+static inline void cp_async_wait_all() { emu::cp_async_wait_all(); }
+#endif
+
+// shared-memory plan of k_ebe_pipe (bytes; every piece 16-byte aligned).  mp = padded maximum of local nodes per tile.
+struct PipeLayout {
+    size_t scratch, data_stride, meta_stride, nodes_off, nst_off, lc_off, inc_off, total;
+    __host__ __device__ explicit PipeLayout(int mp) {
+        scratch = (size_t)3 * TILE_REFS * sizeof(double);
+        data_stride = (size_t)6 * mp * sizeof(double);                         // Xs[3mp] + xs[3mp]
+        nodes_off = 0;
+        nst_off = (size_t)mp * sizeof(int);
+        lc_off = nst_off + (((size_t)mp * sizeof(unsigned short) + 15) & ~(size_t)15);
+        inc_off = lc_off + (size_t)TILE_REFS * sizeof(unsigned short);
+        meta_stride = inc_off + (size_t)TILE_REFS * sizeof(unsigned short);
+        total = scratch + 2 * data_stride + 3 * meta_stride;
+    }
+};
+
+template <int NPC>
+__global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_pipe(const int* __restrict__ tile_off, const int* __restrict__ tile_m, const int* __restrict__ tile_nodes,
+                                                              const unsigned short* __restrict__ lconn, const unsigned short* __restrict__ inc_sorted,
+                                                              const unsigned short* __restrict__ nstart, const double* __restrict__ xq, Material mat,
+                                                              const double* __restrict__ x, double* __restrict__ stage, i64 ne, int ntiles, int mp,
+                                                              const int* done_flag) {
+    const int TE = TILE_REFS / NPC;
+    TOE_DYN_SMEM(unsigned char, smraw, 16);
+    if (done_flag && *done_flag) return;
+    const PipeLayout L(mp);
+    const int tid = threadIdx.x;
+    double* scratch = reinterpret_cast<double*>(smraw);
+    unsigned char* data0 = smraw + L.scratch;
+    unsigned char* meta0 = data0 + 2 * L.data_stride;
+
+    // scalars of the tiles in flight: this one, next, next-but-one (plain loads, always one iteration ahead of their use)
+    int t0 = blockIdx.x, t1 = t0 + gridDim.x, t2 = t1 + gridDim.x;
+    int off0 = 0, m0 = 0, off1 = 0, m1 = 0, off2 = 0, m2 = 0;
+    if (t0 < ntiles) { off0 = __ldg(&tile_off[t0]); m0 = __ldg(&tile_m[t0]); }
+    if (t1 < ntiles) { off1 = __ldg(&tile_off[t1]); m1 = __ldg(&tile_m[t1]); }
+    if (t2 < ntiles) { off2 = __ldg(&tile_off[t2]); m2 = __ldg(&tile_m[t2]); }
+
+    auto issue_meta = [&](int t, int off, int m, int slot) {
+        if (t >= ntiles) return;
+        unsigned char* M = meta0 + (size_t)slot * L.meta_stride;
+        const i64 e0 = (i64)t * TE;
+        const int nel = (int)min((i64)TE, ne - e0);
+        const int nref = nel * NPC;
+        const int n_nodes16 = (m + 3) >> 2, n_nst16 = (m + 7) >> 3, n_ref16 = (nref + 7) >> 3;
+        const unsigned char* gn = reinterpret_cast<const unsigned char*>(tile_nodes + off);
+        const unsigned char* gs = reinterpret_cast<const unsigned char*>(nstart + off);
+        const unsigned char* gl = reinterpret_cast<const unsigned char*>(lconn + e0 * NPC);
+        const unsigned char* gi = reinterpret_cast<const unsigned char*>(inc_sorted + e0 * NPC);
+        for (int k = tid; k < n_nodes16; k += TE) cp_async_16(M + L.nodes_off + 16 * k, gn + 16 * k);
+        for (int k = tid; k < n_nst16; k += TE) cp_async_16(M + L.nst_off + 16 * k, gs + 16 * k);
+        for (int k = tid; k < n_ref16; k += TE) { cp_async_16(M + L.lc_off + 16 * k, gl + 16 * k); cp_async_16(M + L.inc_off + 16 * k, gi + 16 * k); }
+    };
+    auto issue_gather = [&](int t, int m, int mslot, int dslot) {
+        if (t >= ntiles) return;
+        const int* nodes = reinterpret_cast<const int*>(meta0 + (size_t)mslot * L.meta_stride + L.nodes_off);
+        double* Xs = reinterpret_cast<double*>(data0 + (size_t)dslot * L.data_stride);
+        double* xs = Xs + 3 * mp;
+        for (int j = tid; j < m; j += TE) {
+            const int q = nodes[j];
+            const double* gc = xq + 3 * (size_t)q;
+            const double* gx = x + 3 * (size_t)q;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { cp_async_8(Xs + 3 * j + k, gc + k); cp_async_8(xs + 3 * j + k, gx + k); }
+        }
+    };
+
+    // prologue: metadata of the first tile, then its node data together with the metadata of the second
+    issue_meta(t0, off0, m0, 0);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    issue_gather(t0, m0, 0, 0);
+    issue_meta(t1, off1, m1, 1);
+    cp_async_commit();
+    double lam = 0.0, mu = 0.0;                       // material of this thread's cell in the current tile (prefetched one tile ahead)
+    if (t0 < ntiles) { const i64 e = (i64)t0 * TE + tid; if (e < ne) material_at(mat, (int)e, lam, mu); }
+
+    for (int i = 0; t0 < ntiles; i++) {
+        const int ms = i % 3, ds = i & 1;
+        cp_async_wait_all();
+        __syncthreads();                               // node data of tile i and metadata of tile i+1 are in shared memory, tile i-1 is fully consumed
+        issue_meta(t2, off2, m2, (i + 2) % 3);
+        issue_gather(t1, m1, (i + 1) % 3, ds ^ 1);
+        cp_async_commit();
+        const int t3 = t2 + gridDim.x;
+        int off3 = 0, m3 = 0;
+        if (t3 < ntiles) { off3 = __ldg(&tile_off[t3]); m3 = __ldg(&tile_m[t3]); }
+        double lam_n = 0.0, mu_n = 0.0;
+        if (t1 < ntiles) { const i64 e = (i64)t1 * TE + tid; if (e < ne) material_at(mat, (int)e, lam_n, mu_n); }
+
+        // ---- compute tile i (t0) ----
+        const unsigned char* M = meta0 + (size_t)ms * L.meta_stride;
+        const unsigned short* s_nst = reinterpret_cast<const unsigned short*>(M + L.nst_off);
+        const unsigned short* s_lc = reinterpret_cast<const unsigned short*>(M + L.lc_off);
+        const unsigned short* s_inc = reinterpret_cast<const unsigned short*>(M + L.inc_off);
+        const double* Xs = reinterpret_cast<const double*>(data0 + (size_t)ds * L.data_stride);
+        const double* xs = Xs + 3 * mp;
+        const i64 e0 = (i64)t0 * TE;
+        const int nel = (int)min((i64)TE, ne - e0);
+        const int nref = nel * NPC;
+        const int m = m0, off = off0;
+        if (tid < nel) {
+            int l[NPC];
+#pragma unroll
+            for (int a = 0; a < NPC; a++) l[a] = s_lc[NPC * tid + a];
+            if (NPC == 4) {
+                double X[4][3], g[4][3];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) X[a][k] = Xs[3 * l[a] + k];
+                double det = tet_grads(X, g);
+                double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; c2++) {
+                        double xv = xs[3 * l[b] + c2];
+#pragma unroll
+                        for (int i2 = 0; i2 < 3; i2++) H[c2][i2] += xv * g[b][i2];
+                    }
+                double S[3][3]; hooke_from_grad(H, lam, mu, S);
+                double w = det * (1.0 / 6.0);
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; c2++)
+                        scratch[3 * (4 * tid + a) + c2] = w * (S[c2][0] * g[a][0] + S[c2][1] * g[a][1] + S[c2][2] * g[a][2]);
+            } else {
+                double X[8][3], xe[8][3], out[8][3];
+#pragma unroll
+                for (int a = 0; a < 8; a++)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { X[a][k] = Xs[3 * l[a] + k]; xe[a][k] = xs[3 * l[a] + k]; out[a][k] = 0.0; }
+                for (int gp = 0; gp < 8; gp++) {
+                    double g[8][3], N[8];
+                    double det = hex_grads_at(X, gp, g, N);
+                    double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+                    for (int b = 0; b < 8; b++)
+#pragma unroll
+                        for (int c2 = 0; c2 < 3; c2++)
+#pragma unroll
+                            for (int i2 = 0; i2 < 3; i2++) H[c2][i2] += xe[b][c2] * g[b][i2];
+                    double S[3][3]; hooke_from_grad(H, lam, mu, S);
+#pragma unroll
+                    for (int a = 0; a < 8; a++)
+#pragma unroll
+                        for (int c2 = 0; c2 < 3; c2++) out[a][c2] += det * (S[c2][0] * g[a][0] + S[c2][1] * g[a][1] + S[c2][2] * g[a][2]);
+                }
+#pragma unroll
+                for (int a = 0; a < 8; a++)
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; c2++) scratch[3 * (8 * tid + a) + c2] = out[a][c2];
+            }
+        }
+        __syncthreads();
+        for (int j = tid; j < m; j += TE) {
+            int lo = s_nst[j];
+            int hi = j + 1 < m ? (int)s_nst[j + 1] : nref;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int p = lo; p < hi; p++) {
+                int ref = s_inc[p];
+                s0 += scratch[3 * ref]; s1 += scratch[3 * ref + 1]; s2 += scratch[3 * ref + 2];
+            }
+            double* o = stage + 3 * (size_t)(off + j);
+            o[0] = s0; o[1] = s1; o[2] = s2;
+        }
+        // rotate the pipeline registers
+        t0 = t1; off0 = off1; m0 = m1;
+        t1 = t2; off1 = off2; m1 = m2;
+        t2 = t3; off2 = off3; m2 = m3;
+        lam = lam_n; mu = mu_n;
+    }
+    cp_async_wait_all();
+}
+
 template <bool CG>
 __global__ void __launch_bounds__(256) k_ebe_nodes(const int* __restrict__ nst_ptr, const int* __restrict__ nst, const double* __restrict__ stage,
                                                    const unsigned char* __restrict__ dflag, const double* __restrict__ dval, int any_dirichlet,
@@ -299,6 +520,32 @@ __global__ void __launch_bounds__(256) k_ebe_nodes(const int* __restrict__ nst_p
 int ebe_tile_launch(toe_ctx* ctx, const double* x, double* y, CGScalars* cg, bool mask, const int* done_flag, double* dot_out) {
     TRY(mesh_build_tiles(ctx));
     const int npc = ctx->npc;
+    const bool use_pipe = getenv("TOE_EBE_PIPE") != nullptr;                   // pipelined persistent form (opt-in until measured)
+    bool piped = false;
+    if (use_pipe && !mask) {
+        const int mp = (ctx->tile_max_nodes + 7) & ~7;
+        const PipeLayout L(mp);
+        if (L.total <= 200 * 1024) {
+            static size_t pipe_attr[2] = {0, 0};
+            if (L.total > 48 * 1024 && L.total > pipe_attr[npc == 8]) {
+                CU(cudaFuncSetAttribute(k_ebe_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+                CU(cudaFuncSetAttribute(k_ebe_pipe<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+                pipe_attr[npc == 8] = L.total;
+            }
+            int per_sm = (int)((220 * 1024) / (L.total + 1024));
+            const int cap = npc == 4 ? 4 : 8;                                  // 1024 threads per SM at most
+            per_sm = per_sm < 1 ? 1 : (per_sm > cap ? cap : per_sm);
+            unsigned grid = min_u((unsigned)ctx->ntiles, (unsigned)(N_SM * per_sm));
+            if (const char* eg = getenv("TOE_EBE_PIPE_GRID")) { int v = atoi(eg); if (v >= 1 && (unsigned)v < grid) grid = (unsigned)v; }   // tests: several tiles per CTA on small meshes
+#define PIPE_ARGS (const int*)ctx->tile_off.p, (const int*)ctx->tile_m.p, (const int*)ctx->tile_nodes.p, (const unsigned short*)ctx->tile_lconn.p, \
+            (const unsigned short*)ctx->tile_inc.p, (const unsigned short*)ctx->tile_nstart.p, (const double*)ctx->xq.p, ctx->mat, x, ctx->tile_stage.p, ctx->ne, \
+            ctx->ntiles, mp, done_flag
+            if (npc == 4) LAUNCH(ctx, k_ebe_pipe<4>, grid, 256, L.total, PIPE_ARGS);
+            else          LAUNCH(ctx, k_ebe_pipe<8>, grid, 128, L.total, PIPE_ARGS);
+#undef PIPE_ARGS
+            piped = true;
+        }
+    }
     size_t smem = (3 * (size_t)TILE_REFS + 6 * (size_t)ctx->tile_max_nodes) * sizeof(double) + (TILE_REFS + (size_t)ctx->tile_max_nodes + 8) * sizeof(unsigned short);
     static size_t attr_smem[2] = {0, 0};
     if (smem > 48 * 1024 && smem > attr_smem[npc == 8]) {
@@ -308,10 +555,11 @@ int ebe_tile_launch(toe_ctx* ctx, const double* x, double* y, CGScalars* cg, boo
         CU(cudaFuncSetAttribute(k_ebe_tile<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem[npc == 8] = smem;
     }
-#define TILE_ARGS (const int*)ctx->tile_off.p, (const int*)ctx->tile_nodes.p, (const unsigned short*)ctx->tile_lconn.p, (const unsigned short*)ctx->tile_inc.p, \
+#define TILE_ARGS (const int*)ctx->tile_off.p, (const int*)ctx->tile_m.p, (const int*)ctx->tile_nodes.p, (const unsigned short*)ctx->tile_lconn.p, (const unsigned short*)ctx->tile_inc.p, \
         (const unsigned short*)ctx->tile_nstart.p, (const double*)ctx->xq.p, ctx->mat, (const unsigned char*)ctx->dflag.p, x, ctx->tile_stage.p, ctx->ne, done_flag
-    if (npc == 4) { if (mask) LAUNCH(ctx, (k_ebe_tile<4, true>), ctx->ntiles, 256, smem, TILE_ARGS); else LAUNCH(ctx, (k_ebe_tile<4, false>), ctx->ntiles, 256, smem, TILE_ARGS); }
-    else          { if (mask) LAUNCH(ctx, (k_ebe_tile<8, true>), ctx->ntiles, 128, smem, TILE_ARGS); else LAUNCH(ctx, (k_ebe_tile<8, false>), ctx->ntiles, 128, smem, TILE_ARGS); }
+    if (piped) {}
+    else if (npc == 4) { if (mask) LAUNCH(ctx, (k_ebe_tile<4, true>), ctx->ntiles, 256, smem, TILE_ARGS); else LAUNCH(ctx, (k_ebe_tile<4, false>), ctx->ntiles, 256, smem, TILE_ARGS); }
+    else               { if (mask) LAUNCH(ctx, (k_ebe_tile<8, true>), ctx->ntiles, 128, smem, TILE_ARGS); else LAUNCH(ctx, (k_ebe_tile<8, false>), ctx->ntiles, 128, smem, TILE_ARGS); }
 #undef TILE_ARGS
     unsigned grid = div_up(ctx->nq, 256);
 #define NODE_ARGS (const int*)ctx->nst_ptr.p, (const int*)ctx->nst.p, (const double*)ctx->tile_stage.p, (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, \
