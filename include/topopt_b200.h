@@ -120,6 +120,30 @@ int toe_add_nodal_force(toe_ctx* ctx, const int64_t* nodes, int64_t nnodes, cons
 int toe_add_volume_force(toe_ctx* ctx, const double b[3], double rho_uniform, const double* density,
                          double skip_below, double* total_force_out);
 
+/* ---- boundary-node selection and surface traction (SelectNodesForBC.jl, SurfaceTraction.jl) ------------------- */
+/* Two-call pattern: pass nodes_out = NULL to get the count, then a buffer of that many int64 (ascending 1-based ids).
+ * extract_surface_nodes! (SelectNodesForBC.jl:59-123): nodes of the faces that belong to exactly one cell. */
+int toe_surface_nodes(toe_ctx* ctx, int64_t* nodes_out, int64_t* count_out);
+/* select_nodes_by_plane (:325-335 → :146-185): surface nodes with abs(dot(x - point, normal/|normal|)) < tolerance
+ * (the reference's default tolerance is 1.0). */
+int toe_select_nodes_by_plane(toe_ctx* ctx, const double point[3], const double normal[3], double tolerance, int64_t* nodes_out, int64_t* count_out);
+/* select_nodes_by_circle (:357-368 → :207-266): the plane selection, then in-plane distance from center <= radius + tolerance. */
+int toe_select_nodes_by_circle(toe_ctx* ctx, const double center[3], const double normal[3], double radius, double tolerance,
+                               int64_t* nodes_out, int64_t* count_out);
+/* get_boundary_facets (SurfaceTraction.jl:45-66): (cell, local face) pairs, 1-based, Ferrite's facet numbering
+ * (get_face_nodes, FiniteElementAnalysis.jl:42-56), whose vertices ALL lie in `nodes`; ascending.  facets_out = NULL: count only. */
+int toe_boundary_facets(toe_ctx* ctx, const int64_t* nodes, int64_t nnodes, int64_t* facets_out /* 2*capacity */, int64_t capacity, int64_t* count_out);
+/* compute_boundary_area (:88-122): sum of dΓ over FacetQuadratureRule{Ref*}(2) of every facet. */
+int toe_boundary_area(toe_ctx* ctx, const int64_t* facets /* 2*nfacets */, int64_t nfacets, double* area_out);
+/* quadrature points (3 per Tet4 face, 4 per Hex8 face) and dΓ of every facet — what a host callback (x,y,z) -> t needs
+ * (apply_surface_traction! with an arbitrary Julia function, :160-225); either output may be NULL. */
+int toe_facet_quadrature(toe_ctx* ctx, const int64_t* facets, int64_t nfacets, double* xq_out /* 3*nqp*nfacets */, double* dgamma_out /* nqp*nfacets */);
+/* apply_surface_traction! (:160-225): f[celldofs] += Σ_q (N_i · t_q) dΓ_q with t_q = traction_qp (3 per quadrature point, in
+ * the order of toe_facet_quadrature) or, if that is NULL, the constant traction_uniform (apply_uniform_surface_traction!,
+ * :261-287, passes F/area).  area_out / total_force_out[3] (∫dΓ, ∫t dΓ) may be NULL. */
+int toe_add_surface_traction(toe_ctx* ctx, const int64_t* facets, int64_t nfacets, const double* traction_qp, const double traction_uniform[3],
+                             double* area_out, double* total_force_out);
+
 /* ---- Dirichlet: Ferrite apply!(K,f,ch) (call sites :540-542, :841-843, RobustSolver.jl:542-544) ------- */
 /* zero-valued constraints on dofs (1-based): m = mean(abs(diag K)) of the incoming K, stored entries of the
  * prescribed rows and columns become 0.0, K[d,d] = m, f[d] = 0.  Call once per ConstraintHandler, in order. */

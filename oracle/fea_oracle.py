@@ -426,3 +426,118 @@ def calculate_stresses(prob, u, lam, mu):
                  + 3.0 * (s[:, 0, 1] ** 2 + s[:, 1, 2] ** 2 + s[:, 0, 2] ** 2))
     am = int(np.argmax(vm))
     return sig, vm, float(vm[am]), am + 1
+
+
+# ----------------------------------------------------------------------------------------------
+# boundary-node selection and surface traction
+# ----------------------------------------------------------------------------------------------
+# local face tables, 1-based like the reference: get_face_nodes, FiniteElementAnalysis.jl:42-56
+FACE_NODES = {4: [(1, 3, 2), (1, 2, 4), (2, 3, 4), (1, 4, 3)],
+              8: [(1, 4, 3, 2), (1, 2, 6, 5), (2, 3, 7, 6), (3, 4, 8, 7), (1, 5, 8, 4), (5, 6, 7, 8)]}
+
+
+def extract_surface_nodes(cells):
+    """`extract_surface_nodes!` (SelectNodesForBC.jl:59-123): a face (sorted node tuple) that belongs to exactly one cell is a
+    surface face; the surface nodes are the nodes of those faces.  → sorted 1-based node ids (the reference sorts them at :97)."""
+    count = {}
+    npc = cells.shape[1]
+    for cell in cells:
+        for face in FACE_NODES[npc]:
+            key = tuple(sorted(int(cell[i - 1]) for i in face))
+            count[key] = count.get(key, 0) + 1
+    nodes = set()
+    for key, c in count.items():
+        if c == 1:
+            nodes.update(key)
+    return np.array(sorted(nodes), dtype=np.int64)
+
+
+def select_nodes_by_plane(points, cells, point, normal, tolerance=1.0):
+    """`select_nodes_by_plane` → `select_surface_nodes_by_plane` (SelectNodesForBC.jl:146-185, :325-335): surface nodes with
+    abs(dot(x - point, normal/‖normal‖)) < tolerance (default tolerance 1.0, :327).  → sorted 1-based ids."""
+    surf = extract_surface_nodes(cells)
+    n = np.asarray(normal, dtype=np.float64) / np.linalg.norm(normal)
+    d = np.abs((points[surf - 1] - np.asarray(point, dtype=np.float64)) @ n)
+    return surf[d < tolerance]
+
+
+def select_nodes_by_circle(points, cells, center, normal, radius, tolerance=1.0):
+    """`select_nodes_by_circle` → `select_surface_nodes_by_circle` (SelectNodesForBC.jl:207-266, :357-368): nodes of the plane
+    selection whose in-plane distance from the centre is <= radius + tolerance."""
+    on_plane = select_nodes_by_plane(points, cells, center, normal, tolerance)
+    n = np.asarray(normal, dtype=np.float64) / np.linalg.norm(normal)
+    v = points[on_plane - 1] - np.asarray(center, dtype=np.float64)
+    proj = v - np.outer(v @ n, n)
+    return on_plane[np.linalg.norm(proj, axis=1) <= radius + tolerance]
+
+
+def get_boundary_facets(cells, nodes):
+    """`get_boundary_facets` (SurfaceTraction.jl:45-66): every (cell, local face), 1-based, all of whose vertices are in `nodes`
+    — interior faces qualify too, exactly as in the reference.  → (n,2) int64 sorted by (cell, face)."""
+    s = set(int(g) for g in nodes)
+    npc = cells.shape[1]
+    out = []
+    for e, cell in enumerate(cells):
+        for fid, face in enumerate(FACE_NODES[npc]):
+            if all(int(cell[i - 1]) in s for i in face):
+                out.append((e + 1, fid + 1))
+    return np.array(out, dtype=np.int64).reshape(-1, 2)
+
+
+def facet_quadrature(points, cells, facets):
+    """Ferrite `FacetValues(FacetQuadratureRule{Ref*}(2), ip)` as the reference uses it (SurfaceTraction.jl:95-118, 174-204):
+    per facet the quadrature points x_q, dΓ_q = ‖∂x/∂s × ∂x/∂t‖ w_q and the values N_a(x_q) of the cell's shape functions.
+    Tet4 face: 3-point rule of the triangle (barycentric (2/3,1/6,1/6) permutations, w = 1/6 on the reference triangle of area
+    1/2) — point k sits next to face vertex k; Hex8 face: 2x2 Gauss on the bilinear quadrilateral in the face's node order.
+    → (xq (nf,nqp,3), dgamma (nf,nqp), N (nf,nqp,npc))."""
+    npc = cells.shape[1]
+    nf = len(facets)
+    nqp = 3 if npc == 4 else 4
+    xq = np.zeros((nf, nqp, 3)); dg = np.zeros((nf, nqp)); N = np.zeros((nf, nqp, npc))
+    g = 1.0 / np.sqrt(3.0)
+    for i, (e, fid) in enumerate(facets):
+        loc = [a - 1 for a in FACE_NODES[npc][fid - 1]]
+        P = points[cells[e - 1, loc] - 1]
+        if npc == 4:
+            nvec = np.cross(P[1] - P[0], P[2] - P[0])
+            for k in range(3):
+                w = np.full(3, 1.0 / 6.0); w[k] = 2.0 / 3.0
+                xq[i, k] = w @ P
+                dg[i, k] = np.linalg.norm(nvec) / 6.0
+                N[i, k, loc] = w
+        else:
+            for k, (s, t) in enumerate(((-g, -g), (g, -g), (g, g), (-g, g))):
+                Nf = 0.25 * np.array([(1 - s) * (1 - t), (1 + s) * (1 - t), (1 + s) * (1 + t), (1 - s) * (1 + t)])
+                dNs = 0.25 * np.array([-(1 - t), (1 - t), (1 + t), -(1 + t)])
+                dNt = 0.25 * np.array([-(1 - s), -(1 + s), (1 + s), (1 - s)])
+                xq[i, k] = Nf @ P
+                dg[i, k] = np.linalg.norm(np.cross(dNs @ P, dNt @ P))
+                N[i, k, loc] = Nf
+    return xq, dg, N
+
+
+def compute_boundary_area(points, cells, facets):
+    """`compute_boundary_area` (SurfaceTraction.jl:88-122): Σ dΓ over the facets' quadrature points."""
+    return float(facet_quadrature(points, cells, facets)[1].sum())
+
+
+def apply_surface_traction(prob, facets, traction_function):
+    """`apply_surface_traction!` (SurfaceTraction.jl:160-225): f[celldofs] += Σ_q (N_i · t(x_q)) dΓ_q.  → (area, total force)."""
+    xq, dg, N = facet_quadrature(prob.points, prob.cells, facets)
+    total = np.zeros(3); area = 0.0
+    for i, (e, fid) in enumerate(facets):
+        cd = prob.cell_dofs[e - 1].reshape(-1, 3)
+        for k in range(xq.shape[1]):
+            t = np.asarray(traction_function(*xq[i, k]), dtype=np.float64)
+            prob.f[cd - 1] += N[i, k][:, None] * t[None, :] * dg[i, k]
+            total += t * dg[i, k]; area += dg[i, k]
+    return area, total
+
+
+def apply_uniform_surface_traction(prob, facets, total_force_vector):
+    """`apply_uniform_surface_traction!` (SurfaceTraction.jl:261-287): t = F / area (error if area < 1e-12), then the above."""
+    area = compute_boundary_area(prob.points, prob.cells, facets)
+    if area < 1e-12:
+        raise ValueError("Boundary area is effectively zero. Check facet selection.")
+    t = np.asarray(total_force_vector, dtype=np.float64) / area
+    return apply_surface_traction(prob, facets, lambda x, y, z: t)

@@ -69,3 +69,8 @@ def test_pipelined_matrix_free_operator(ctx, pkg):
     import ebe_pipe_checks as pc
     pc.check_pipe_equals_tile(pkg, ctx, [((30, 3, 2), False), ((40, 4, 3), False), ((33, 5, 4), True)], grids=(None, 1, 2, 3, 5), solve=False)
     pc.check_pipe_equals_tile(pkg, ctx, [((8, 3, 2), False), ((6, 3, 2), True)], grids=(None, 1), solve=True)
+
+
+def test_boundary_selection_and_surface_traction(pkg, fo, golden_c1):
+    import surface_checks as sc
+    sc.check_surface(pkg, fo, golden_c1)

@@ -24,3 +24,10 @@ def test_pipelined_matrix_free_operator_equals_tile_kernel(pkg):
         pc.check_pipe_equals_tile(pkg, ctx, [((24, 8, 4), False)], grids=(None, 3), solve=True)
     finally:
         ctx.close()
+
+
+def test_boundary_selection_and_surface_traction(pkg, fo, golden_c1):
+    """SURVEY §8(f) next-row 3 on the GPU: surface extraction, plane / circle selection, facets, area, uniform and callback
+    traction — against the oracle's literal restatement of SelectNodesForBC.jl / SurfaceTraction.jl."""
+    import surface_checks as sc
+    sc.check_surface(pkg, fo, golden_c1)

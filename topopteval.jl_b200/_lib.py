@@ -70,6 +70,13 @@ SIGNATURES = {
     "toe_set_rhs": (C.c_int, [_P, _D]),
     "toe_add_nodal_force": (C.c_int, [_P, _I64, C.c_int64, _D]),
     "toe_add_volume_force": (C.c_int, [_P, _D, C.c_double, _D, C.c_double, _D]),
+    "toe_surface_nodes": (C.c_int, [_P, _I64, _I64]),
+    "toe_select_nodes_by_plane": (C.c_int, [_P, _D, _D, C.c_double, _I64, _I64]),
+    "toe_select_nodes_by_circle": (C.c_int, [_P, _D, _D, C.c_double, C.c_double, _I64, _I64]),
+    "toe_boundary_facets": (C.c_int, [_P, _I64, C.c_int64, _I64, C.c_int64, _I64]),
+    "toe_boundary_area": (C.c_int, [_P, _I64, C.c_int64, _D]),
+    "toe_facet_quadrature": (C.c_int, [_P, _I64, C.c_int64, _D, _D]),
+    "toe_add_surface_traction": (C.c_int, [_P, _I64, C.c_int64, _D, _D, _D, _D]),
     "toe_apply_dirichlet": (C.c_int, [_P, _I64, C.c_int64, _D]),
     "toe_solve_pcg": (C.c_int, [_P, C.c_double, C.c_double, C.c_int64, C.c_int, C.POINTER(PcgStats), _D, C.c_int64]),
     "toe_get_solution": (C.c_int, [_P, _D]),
@@ -260,6 +267,64 @@ class Context:
         d = None if density is None else f64(density)
         self._ck(self.lib.toe_add_volume_force(self.h, _dp(b), float(rho_uniform), _dp(d), float(skip_below), _dp(tot)))
         return tot
+
+    # -- boundary-node selection / surface traction (SelectNodesForBC.jl, SurfaceTraction.jl) ------------------
+    def _select(self, fn, *args):
+        n = C.c_int64()
+        self._ck(fn(self.h, *args, None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.int64)
+        if n.value:
+            self._ck(fn(self.h, *args, _ip(out), C.byref(n)))
+        return out
+
+    def surface_nodes(self):
+        return self._select(self.lib.toe_surface_nodes)
+
+    def select_nodes_by_plane(self, point, normal, tolerance=1.0):
+        point = f64(point); normal = f64(normal)
+        return self._select(self.lib.toe_select_nodes_by_plane, _dp(point), _dp(normal), float(tolerance))
+
+    def select_nodes_by_circle(self, center, normal, radius, tolerance=1.0):
+        center = f64(center); normal = f64(normal)
+        return self._select(self.lib.toe_select_nodes_by_circle, _dp(center), _dp(normal), float(radius), float(tolerance))
+
+    def boundary_facets(self, nodes):
+        nodes = i64(sorted(nodes) if isinstance(nodes, (set, frozenset)) else nodes)
+        n = C.c_int64()
+        self._ck(self.lib.toe_boundary_facets(self.h, _ip(nodes) if nodes.size else None, nodes.size, None, 0, C.byref(n)))
+        out = np.empty((n.value, 2), dtype=np.int64)
+        if n.value:
+            self._ck(self.lib.toe_boundary_facets(self.h, _ip(nodes), nodes.size, _ip(out), n.value, C.byref(n)))
+        return out
+
+    @staticmethod
+    def _facets(facets):
+        if isinstance(facets, (set, frozenset)):
+            facets = sorted(facets)
+        return i64(np.asarray(facets, dtype=np.int64).reshape(-1, 2))
+
+    def boundary_area(self, facets):
+        facets = self._facets(facets)
+        a = C.c_double()
+        self._ck(self.lib.toe_boundary_area(self.h, _ip(facets) if facets.size else None, facets.shape[0], C.byref(a)))
+        return a.value
+
+    def facet_quadrature(self, facets):
+        facets = self._facets(facets)
+        nqp = 3 if self.npc == 4 else 4
+        xq = np.empty((facets.shape[0], nqp, 3)); dg = np.empty((facets.shape[0], nqp))
+        self._ck(self.lib.toe_facet_quadrature(self.h, _ip(facets) if facets.size else None, facets.shape[0], _dp(xq), _dp(dg)))
+        return xq, dg
+
+    def add_surface_traction(self, facets, traction_qp=None, traction_uniform=None):
+        facets = self._facets(facets)
+        tq = None if traction_qp is None else f64(traction_qp)
+        tu = None if traction_uniform is None else f64(traction_uniform)
+        if tq is not None and tq.size != 3 * (3 if self.npc == 4 else 4) * facets.shape[0]:
+            raise TopOptError("traction_qp must hold 3 values per quadrature point of every facet")
+        a = C.c_double(); tot = np.zeros(3)
+        self._ck(self.lib.toe_add_surface_traction(self.h, _ip(facets) if facets.size else None, facets.shape[0], _dp(tq), _dp(tu), C.byref(a), _dp(tot)))
+        return a.value, tot
 
     def apply_dirichlet(self, dofs):
         dofs = i64(dofs)

@@ -27,6 +27,8 @@ __all__ = [
     "apply_volume_force", "apply_gravity", "apply_acceleration", "apply_variable_density_volume_force",
     "solve_system", "solve_system_simp", "solve_system_robust", "solve_system_robust_simp", "solve_system_adaptive",
     "SolverConfig", "export_results", "TopOptError",
+    "select_nodes_by_plane", "select_nodes_by_circle", "get_node_dofs",
+    "get_boundary_facets", "compute_boundary_area", "apply_surface_traction", "apply_uniform_surface_traction",
 ]
 
 
@@ -163,6 +165,8 @@ def setup_problem(grid: Grid, interpolation_order: int = 1, device: int = 0, ctx
     n = ctx.build_dofs()
     print("Number of DOFs: %d" % n)
     ctx.build_pattern()
+    if not distributed:
+        grid._ctx = ctx                       # boundary-node selection on this grid reuses the device copy of the mesh
     return DofHandler(ctx, grid), CellValues(npc, 4 if npc == 4 else 8), StiffnessMatrix(ctx), LoadVector(ctx)
 
 
@@ -252,6 +256,103 @@ def apply_variable_density_volume_force(f, dh, cellvalues, body_force_vector, de
     print("Applied variable density volume force")
     print("Total force applied: %s N" % list(tot))
     return tot
+
+
+# ------------------------------------------------------------------------------------------------------
+# boundary-node selection (SelectNodesForBC.jl) and surface traction (SurfaceTraction.jl)
+# ------------------------------------------------------------------------------------------------------
+def _grid_ctx(grid: Grid) -> Context:
+    """The reference caches the surface nodes per grid (GRID_CACHE_STORAGE, SelectNodesForBC.jl:271-301); here the grid keeps
+    the ctx that holds its mesh (set by setup_problem, or created on first use)."""
+    ctx = getattr(grid, "_ctx", None)
+    if ctx is None or getattr(ctx, "h", None) is None:
+        ctx = Context(0)
+        ctx.set_mesh(grid.nodes, grid.cells)
+        ctx.build_dofs()
+        ctx.build_pattern()
+        grid._ctx = ctx
+    return ctx
+
+
+def select_nodes_by_plane(grid: Grid, point, normal, tolerance: float = 1.0):
+    """SelectNodesForBC.jl:325-335 — surface nodes on the plane (point, normal); `tolerance` defaults to 1.0 like the reference."""
+    nodes = _grid_ctx(grid).select_nodes_by_plane(point, normal, tolerance)
+    print("Selected %d surface nodes on the specified plane" % nodes.size)
+    return set(int(g) for g in nodes)
+
+
+def select_nodes_by_circle(grid: Grid, center, normal, radius: float, tolerance: float = 1.0):
+    """SelectNodesForBC.jl:357-368."""
+    nodes = _grid_ctx(grid).select_nodes_by_circle(center, normal, radius, tolerance)
+    print("Selected %d surface nodes in the circular region" % nodes.size)
+    return set(int(g) for g in nodes)
+
+
+class NodeDofs:
+    """`get_node_dofs(dh)` (FiniteElementAnalysis.jl:265-293): node id -> its DOFs, as a read-only mapping over the device-built
+    DOF map (the reference builds a Dict by sweeping all cells)."""
+
+    def __init__(self, node_first_dof, dofs_per_node=3):
+        self._first, self._n = node_first_dof, dofs_per_node
+
+    def __contains__(self, node):
+        return 1 <= node <= self._first.size and self._first[node - 1] > 0
+
+    def __getitem__(self, node):
+        if node not in self:
+            raise KeyError(node)
+        d = int(self._first[node - 1])
+        return [d + k for k in range(self._n)]
+
+    def __len__(self):
+        return int(np.count_nonzero(self._first))
+
+    def keys(self):
+        return (np.nonzero(self._first)[0] + 1).tolist()
+
+
+def get_node_dofs(dh):
+    return NodeDofs(dh.node_first_dof)
+
+
+def get_boundary_facets(grid: Grid, nodes):
+    """SurfaceTraction.jl:45-66 → (n,2) int64 array of (cell_id, local_face_id), 1-based, ascending (the reference returns a Set)."""
+    facets = _grid_ctx(grid).boundary_facets(nodes)
+    print("Found %d boundary facets" % facets.shape[0])
+    return facets
+
+
+def compute_boundary_area(grid: Grid, dh, boundary_facets) -> float:
+    """SurfaceTraction.jl:88-122."""
+    return dh.ctx.boundary_area(boundary_facets)
+
+
+def apply_surface_traction(f, dh, grid: Grid, boundary_facets, traction_function):
+    """SurfaceTraction.jl:160-225: the callback (x, y, z) -> [Tx, Ty, Tz] is evaluated on the host at the facets' quadrature
+    points; the quadrature itself and the scatter into f run on the GPU."""
+    ctx = dh.ctx
+    xq, _ = ctx.facet_quadrature(boundary_facets)
+    tq = np.array([[np.asarray(traction_function(*x), dtype=np.float64) for x in fx] for fx in xq]).reshape(xq.shape)
+    area, total = ctx.add_surface_traction(boundary_facets, traction_qp=tq)
+    print("Applied surface traction over %d facets" % xq.shape[0])
+    print("  Total boundary area: %s" % round(area, 6))
+    print("  Total applied force: %s" % [round(float(v), 6) for v in total])
+    return area, total
+
+
+def apply_uniform_surface_traction(f, dh, grid: Grid, boundary_facets, total_force_vector):
+    """SurfaceTraction.jl:261-287: t = F_total / area, error when the area is effectively zero."""
+    ctx = dh.ctx
+    area = ctx.boundary_area(boundary_facets)
+    if area < 1e-12:
+        raise TopOptError("Boundary area is effectively zero. Check facet selection.")
+    traction = np.asarray(total_force_vector, dtype=np.float64) / area
+    print("Uniform surface traction:")
+    print("  Boundary area: %s" % round(area, 6))
+    print("  Traction magnitude: %s" % round(float(np.linalg.norm(traction)), 6))
+    area, total = ctx.add_surface_traction(boundary_facets, traction_uniform=traction)
+    print("Applied surface traction over %d facets" % len(boundary_facets))
+    return area, total
 
 
 # ------------------------------------------------------------------------------------------------------

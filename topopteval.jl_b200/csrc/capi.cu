@@ -34,6 +34,11 @@ int dist_node_dofs(toe_ctx* ctx, const int** node_q_g);
 i64 dist_global_ne(toe_ctx* ctx);
 i64 dist_global_ndofs(toe_ctx* ctx);
 
+int select_nodes(toe_ctx* ctx, int mode, const double* point, const double* normal, double radius, double tol, int64_t* nodes_out, int64_t* count_out);
+int boundary_facets(toe_ctx* ctx, const int64_t* nodes, i64 nnodes, int64_t* facets_out, i64 capacity, int64_t* count_out);
+int facet_integrals(toe_ctx* ctx, const int64_t* facets, i64 nf, double* xq_out, double* dg_out, int add_load, const double* t_qp, const double* t_uniform,
+                    double* area_out, double* total_force_out);
+
 static std::string g_create_error;
 static std::mutex g_mutex;
 
@@ -281,6 +286,27 @@ int toe_energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_e
 int toe_energy_assembled(toe_ctx* ctx, double* half_uKu) { GUARD(ctx); return energy_assembled(ctx, half_uKu); }
 int toe_stresses(toe_ctx* ctx, double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell) {
     GUARD(ctx); return stresses(ctx, sigma, von_mises, max_von_mises, max_stress_cell);
+}
+
+int toe_surface_nodes(toe_ctx* ctx, int64_t* nodes_out, int64_t* count_out) { GUARD(ctx); return select_nodes(ctx, 0, nullptr, nullptr, 0.0, 0.0, nodes_out, count_out); }
+int toe_select_nodes_by_plane(toe_ctx* ctx, const double point[3], const double normal[3], double tolerance, int64_t* nodes_out, int64_t* count_out) {
+    GUARD(ctx); return select_nodes(ctx, 1, point, normal, 0.0, tolerance, nodes_out, count_out);
+}
+int toe_select_nodes_by_circle(toe_ctx* ctx, const double center[3], const double normal[3], double radius, double tolerance, int64_t* nodes_out, int64_t* count_out) {
+    GUARD(ctx); return select_nodes(ctx, 2, center, normal, radius, tolerance, nodes_out, count_out);
+}
+int toe_boundary_facets(toe_ctx* ctx, const int64_t* nodes, int64_t nnodes, int64_t* facets_out, int64_t capacity, int64_t* count_out) {
+    GUARD(ctx); return boundary_facets(ctx, nodes, nnodes, facets_out, capacity, count_out);
+}
+int toe_boundary_area(toe_ctx* ctx, const int64_t* facets, int64_t nfacets, double* area_out) {
+    GUARD(ctx); return facet_integrals(ctx, facets, nfacets, nullptr, nullptr, 0, nullptr, nullptr, area_out, nullptr);
+}
+int toe_facet_quadrature(toe_ctx* ctx, const int64_t* facets, int64_t nfacets, double* xq_out, double* dgamma_out) {
+    GUARD(ctx); return facet_integrals(ctx, facets, nfacets, xq_out, dgamma_out, 0, nullptr, nullptr, nullptr, nullptr);
+}
+int toe_add_surface_traction(toe_ctx* ctx, const int64_t* facets, int64_t nfacets, const double* traction_qp, const double traction_uniform[3],
+                             double* area_out, double* total_force_out) {
+    GUARD(ctx); return facet_integrals(ctx, facets, nfacets, nullptr, nullptr, 1, traction_qp, traction_uniform, area_out, total_force_out);
 }
 
 int toe_spmv(toe_ctx* ctx, const double* x, double* y, int matrix_free) {

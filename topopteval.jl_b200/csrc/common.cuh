@@ -117,6 +117,10 @@ struct toe_ctx {
     // K values: 9 planes of nnzb doubles, plane k = 3*c+d holds K[3q+c, 3q'+d] of block slot s at val[k*nnzb+s]
     DevBuf<double> val;
 
+    // boundary-node selection (surface.cu): 1 = node lies on a face that belongs to exactly one cell
+    DevBuf<int> surf_flag;
+    bool have_surface = false;
+
     // material
     Material mat = {};
     DevBuf<double> density, lam_e, mu_e;

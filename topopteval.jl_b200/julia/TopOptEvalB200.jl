@@ -25,7 +25,9 @@ export setup_problem, create_material_model, create_simp_material_model,
        apply_fixed_boundary!, apply_sliding_boundary!, apply_force!,
        apply_volume_force!, apply_gravity!, apply_acceleration!, apply_variable_density_volume_force!,
        solve_system, solve_system_simp, solve_system_robust, solve_system_robust_simp, solve_system_adaptive,
-       SolverConfig, element_energies, compliance
+       SolverConfig, element_energies, compliance,
+       select_nodes_by_plane, select_nodes_by_circle, get_node_dofs, get_boundary_facets, compute_boundary_area,
+       apply_surface_traction!, apply_uniform_surface_traction!
 
 const LIB = get(ENV, "TOPOPT_B200_LIB", joinpath(@__DIR__, "..", "libtopopt_b200.so"))
 
@@ -106,6 +108,7 @@ function setup_problem(grid::Grid, interpolation_order::Int = 1; device::Integer
     nfd = Vector{Int}(undef, nn)
     check(ctx, ccall((:toe_get_node_dofs, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), ctx.ptr, nfd))
     dh = B200DofHandler(ctx, grid, nd[], nfd)
+    GRID_CTX[objectid(grid)] = ctx                                          # boundary-node selection on this grid reuses the device mesh
     return dh, B200CellValues(npc, npc == 4 ? 4 : 8), B200Matrix(ctx, nd[], nnz[]), B200Vector(ctx, nd[])
 end
 
@@ -241,6 +244,71 @@ function solve_system_adaptive(K, f, dh, cv, λ, μ, constraints...)
     n < 50000 && return solve_system(K, f, dh, cv, λ, μ, constraints...)                     # :574-575
     cfg = SolverConfig(method = :auto, tolerance = 1e-7, max_iterations = min(max(n ÷ 10, 5000), 50000), history = true)
     return solve_system_robust(K, f, dh, cv, λ, μ, constraints...; config = cfg)
+end
+
+# ---- boundary-node selection (SelectNodesForBC.jl) and surface traction (SurfaceTraction.jl) ----------------------------------
+# The reference caches the surface nodes per grid (GRID_CACHE_STORAGE, SelectNodesForBC.jl:271-301); here the ctx that holds the
+# grid's mesh is remembered per grid object (set by setup_problem).
+const GRID_CTX = Dict{UInt,Ctx}()
+function _grid_ctx(grid::Grid)
+    haskey(GRID_CTX, objectid(grid)) && return GRID_CTX[objectid(grid)]
+    dh, _, _, _ = setup_problem(grid)
+    return dh.ctx
+end
+function select_nodes_by_plane(grid::Grid, point::Vector{Float64}, normal::Vector{Float64}, tolerance::Float64 = 1.0)     # :325-335
+    c = _grid_ctx(grid); n = Ref{Int64}(0)
+    check(c, ccall((:toe_select_nodes_by_plane, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Int64}, Ref{Int64}), c.ptr, point, normal, tolerance, C_NULL, n))
+    out = Vector{Int}(undef, n[])
+    n[] > 0 && check(c, ccall((:toe_select_nodes_by_plane, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Int64}, Ref{Int64}), c.ptr, point, normal, tolerance, out, n))
+    println("Selected $(length(out)) surface nodes on the specified plane")
+    return Set{Int}(out)
+end
+function select_nodes_by_circle(grid::Grid, center::Vector{Float64}, normal::Vector{Float64}, radius::Float64, tolerance::Float64 = 1.0)   # :357-368
+    c = _grid_ctx(grid); n = Ref{Int64}(0)
+    check(c, ccall((:toe_select_nodes_by_circle, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Int64}, Ref{Int64}), c.ptr, center, normal, radius, tolerance, C_NULL, n))
+    out = Vector{Int}(undef, n[])
+    n[] > 0 && check(c, ccall((:toe_select_nodes_by_circle, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Int64}, Ref{Int64}), c.ptr, center, normal, radius, tolerance, out, n))
+    println("Selected $(length(out)) surface nodes in the circular region")
+    return Set{Int}(out)
+end
+"get_node_dofs(dh) (:265-293): node id → its 3 DOFs, from the device-built map instead of a sweep over all cells."
+get_node_dofs(dh::B200DofHandler) = Dict{Int,Vector{Int}}(g => [d, d + 1, d + 2] for (g, d) in enumerate(dh.node_first_dof) if d > 0)
+function get_boundary_facets(grid::Grid, nodes::Set{Int})                                                  # SurfaceTraction.jl:45-66
+    c = _grid_ctx(grid); v = sort!(collect(nodes)); n = Ref{Int64}(0)
+    check(c, ccall((:toe_boundary_facets, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ref{Int64}), c.ptr, v, length(v), C_NULL, 0, n))
+    out = Matrix{Int64}(undef, 2, n[])
+    n[] > 0 && check(c, ccall((:toe_boundary_facets, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ref{Int64}), c.ptr, v, length(v), out, n[], n))
+    println("Found $(n[]) boundary facets")
+    return Set{Tuple{Int,Int}}((out[1, i], out[2, i]) for i in 1:n[])
+end
+_facet_matrix(facets) = (v = sort!(collect(facets)); m = Matrix{Int64}(undef, 2, length(v)); for (i, (c, f)) in enumerate(v); m[1, i] = c; m[2, i] = f; end; m)
+function compute_boundary_area(grid::Grid, dh::B200DofHandler, boundary_facets)                            # :88-122
+    m = _facet_matrix(boundary_facets); a = Ref(0.0)
+    check(dh.ctx, ccall((:toe_boundary_area, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ref{Float64}), dh.ctx.ptr, m, size(m, 2), a)); a[]
+end
+function apply_surface_traction!(f, dh::B200DofHandler, grid::Grid, boundary_facets, traction_function::Function)   # :160-225
+    m = _facet_matrix(boundary_facets); nf = size(m, 2)
+    nqp = typeof(getcells(grid, 1)) <: Ferrite.Hexahedron ? 4 : 3
+    xq = Array{Float64}(undef, 3, nqp, nf)
+    check(dh.ctx, ccall((:toe_facet_quadrature, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Float64}), dh.ctx.ptr, m, nf, xq, C_NULL))
+    tq = similar(xq)
+    for i in 1:nf, q in 1:nqp; tq[:, q, i] .= traction_function(xq[1, q, i], xq[2, q, i], xq[3, q, i]); end    # the callback stays on the host
+    area = Ref(0.0); total = zeros(3)
+    check(dh.ctx, ccall((:toe_add_surface_traction, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
+                        dh.ctx.ptr, m, nf, tq, C_NULL, area, total))
+    println("Applied surface traction over $(nf) facets")
+    println("  Total boundary area: $(round(area[], digits=6))")
+    println("  Total applied force: [$(round(total[1], digits=6)), $(round(total[2], digits=6)), $(round(total[3], digits=6))]")
+end
+function apply_uniform_surface_traction!(f, dh::B200DofHandler, grid::Grid, boundary_facets, total_force_vector::Vector{Float64})   # :261-287
+    area = compute_boundary_area(grid, dh, boundary_facets)
+    area < 1e-12 && error("Boundary area is effectively zero. Check facet selection.")
+    traction = total_force_vector ./ area
+    println("Uniform surface traction:"); println("  Boundary area: $(round(area, digits=6))"); println("  Traction magnitude: $(round(sqrt(sum(abs2, traction)), digits=6))")
+    m = _facet_matrix(boundary_facets); a = Ref(0.0); total = zeros(3)
+    check(dh.ctx, ccall((:toe_add_surface_traction, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
+                        dh.ctx.ptr, m, size(m, 2), C_NULL, traction, a, total))
+    println("Applied surface traction over $(size(m, 2)) facets")
 end
 
 # ---- north-star outputs the reference does not have: per-element energies and compliance ------------------------------------------
