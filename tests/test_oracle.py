@@ -3,6 +3,7 @@ tests/golden/make_golden.py), internal consistency of the restatement, and the r
 import hashlib
 
 import numpy as np
+import pytest
 
 
 def sha(a):
@@ -130,3 +131,36 @@ def test_c_oracle_hex_simp(fo, golden_c2):
     lam, mu = fo.create_simp_material_model(1.0, 0.3, 1e-8, 3.0)(rho)
     ke_n = fo.element_stiffness(pts, cells[100:108], lam[100:108], mu[100:108])
     assert np.max(np.abs(ke_c - ke_n)) <= 1e-13 * np.abs(ke_n).max()
+
+
+@pytest.mark.parametrize("hexm", [False, True])
+def test_boundary_selection_and_traction_known_answers(pkg, fo, hexm):
+    """SelectNodesForBC.jl / SurfaceTraction.jl restatement on a box where the answers are known in closed form."""
+    nx, ny, nz = 6, 3, 2
+    pts, cells = pkg.meshgen.cantilever(nx, ny, nz, hex=hexm)
+    surf = fo.extract_surface_nodes(cells)
+    on_box = np.nonzero(np.any((np.abs(pts) < 1e-9) | (np.abs(pts - np.array([60.0, 20.0, 4.0])) < 1e-9), axis=1))[0] + 1
+    assert np.array_equal(surf, on_box) and surf.size == (nx + 1) * (ny + 1) * (nz + 1) - (nx - 1) * (ny - 1) * (nz - 1)
+    tip = fo.select_nodes_by_plane(pts, cells, [60.0, 0.0, 0.0], [3.0, 0.0, 0.0], 1e-6)          # normal is normalised (:164)
+    assert np.array_equal(tip, pkg.meshgen.nodes_at_plane(pts, 0, 60.0))
+    # default tolerance 1.0 (:327): on this mesh (hx = 10) still only the plane itself
+    assert np.array_equal(fo.select_nodes_by_plane(pts, cells, [60.0, 0.0, 0.0], [1.0, 0.0, 0.0]), tip)
+    circ = fo.select_nodes_by_circle(pts, cells, [60.0, 10.0, 2.0], [1.0, 0.0, 0.0], 4.0, 1e-6)
+    d = np.linalg.norm(pts[tip - 1][:, 1:] - np.array([10.0, 2.0]), axis=1)
+    assert np.array_equal(circ, tip[d <= 4.0 + 1e-6])
+    facets = fo.get_boundary_facets(cells, tip)
+    assert len(facets) == (ny * nz if hexm else 2 * ny * nz)
+    assert abs(fo.compute_boundary_area(pts, cells, facets) - 80.0) < 1e-10
+    prob = fo.setup_problem(pts, cells)
+    area, total = fo.apply_uniform_surface_traction(prob, facets, [0.0, 0.0, -1.0])
+    assert abs(area - 80.0) < 1e-10 and np.allclose(total, [0.0, 0.0, -1.0], atol=1e-13)
+    fz = prob.f.reshape(-1, 3)
+    assert abs(fz[:, 2].sum() + 1.0) < 1e-13 and np.abs(fz[:, :2]).max() == 0.0
+    loaded = np.nonzero(np.abs(fz[:, 2]) > 0)[0]
+    assert loaded.size == tip.size                                  # consistent nodal loads live on the tip nodes only
+    # linear traction t_z = z integrates exactly with the order-2 facet rules: ∫ z dΓ = 20 * 4² / 2
+    prob.f[:] = 0.0
+    _, tot = fo.apply_surface_traction(prob, facets, lambda x, y, z: [0.0, 0.0, z])
+    assert abs(tot[2] - 160.0) < 1e-10 and abs(prob.f.sum() - 160.0) < 1e-10
+    with pytest.raises(ValueError):
+        fo.apply_uniform_surface_traction(prob, fo.get_boundary_facets(cells, []), [0.0, 0.0, -1.0])
