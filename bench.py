@@ -274,6 +274,19 @@ def run_b200(args, pkg):
     dev_s, wall_s, clocks, launches = m["dev_s"], m["wall_s"], m["clocks"], m["launches"]
     value = ne_total * args.steps / dev_s
 
+    # extra, outside the timed region and not part of `value`: the same solve with the two-level preconditioner
+    two_level = None
+    if world == 1 and not args.no_two_level:
+        try:
+            st_tl = ctx.solve_pcg(TOL, TOL, ITMAX, matrix_free=mf, two_level=True)
+            e_tl, _, _ = ctx.energy()
+            two_level = {"pcg_seconds": st_tl["solve_seconds"], "pcg_iterations": int(st_tl["niter"]), "converged": bool(st_tl["converged"]),
+                         "coarse_dofs": int(st_tl["coarse_dofs"]), "coarse_operator_seconds": st_tl["precond_seconds"], "energy": e_tl,
+                         "energy_rel_diff_vs_jacobi": abs(e_tl - e) / abs(e), "jacobi_pcg_seconds": stage_acc["solve"] / args.steps,
+                         "note": "M^-1 = D^-1 + Z (Z'KZ)^-1 Z', Z = rigid-body modes of a box grid; reported next to the Jacobi headline, not in it"}
+        except Exception as ex:  # noqa: BLE001 — an optional extra must never cost the headline number
+            two_level = {"error": str(ex)[:300]}
+
     # dominant kernel (SpMV inside PCG): live CUDA-event timing of back-to-back launches on the library's stream
     spmv_s, spmv_bytes = ctx.time_spmv(matrix_free=mf, reps=20)
     spmv_s = max_over_ranks(spmv_s)
@@ -335,7 +348,8 @@ def run_b200(args, pkg):
                        "pcg_iterations": int(st["niter"]), "pcg_converged": bool(st["converged"]), "pcg_rel_res_l2": st["rel_res_l2"], "pcg_restarts": restarts,
                        "spmv_gbs": spmv_bytes / spmv_s / 1e9, "energy_ms": 1e3 * stage_acc["energy"] / args.steps,
                        "energy": e, "compliance": c, "local_sizes": sizes,
-                       "setup_ms": {k: 1e3 * tm_setup[k] for k in ("set_mesh", "build_dofs", "build_pattern")}},
+                       "setup_ms": {k: 1e3 * tm_setup[k] for k in ("set_mesh", "build_dofs", "build_pattern")},
+                       "two_level_preconditioner": two_level},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_step(pkg, CPU_SAMPLE)
@@ -367,6 +381,7 @@ def main():
     ap.add_argument("--workload", default="C4_10M", choices=sorted(WORKLOADS))
     ap.add_argument("--matrix-free", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-two-level", action="store_true", help="skip the extra two-level-preconditioner solve reported in stages")
     args = ap.parse_args()
     import __graft_entry__ as graft
     pkg = graft.load_package()

@@ -43,6 +43,9 @@ typedef struct toe_ctx toe_ctx;
 /* toe_solve_pcg flags */
 #define TOE_PCG_MATRIX_FREE   1   /* element-by-element operator, K is not read (nor needed) */
 #define TOE_PCG_NO_GRAPH      2   /* launch kernels directly instead of replaying a CUDA graph */
+#define TOE_PCG_TWO_LEVEL     4   /* preconditioner M⁻¹ = D⁻¹ + Z(ZᵀKZ)⁻¹Zᵀ instead of Jacobi: Z = rigid-body modes of the boxes of a
+                                     coarse grid over the mesh (≤ 6144 coarse unknowns); same stopping rule on sqrt(r'Mr).
+                                     SolverConfig.preconditioner = :two_level in the shims; single GPU only for now */
 
 typedef struct toe_pcg_stats {
     int64_t niter;            /* Krylov.jl stats.niter */
@@ -56,6 +59,8 @@ typedef struct toe_pcg_stats {
     double  spmv_bytes;       /* algorithmic bytes of one operator application */
     int64_t kernel_launches;  /* kernels launched by this call */
     int64_t restarts;         /* partitioned runs only: solves restarted after a CG breakdown (0 normally) */
+    int64_t coarse_dofs;      /* TOE_PCG_TWO_LEVEL: size of the coarse space (0 otherwise) */
+    double  precond_seconds;  /* TOE_PCG_TWO_LEVEL: device time spent building ZᵀKZ and its inverse (part of solve_seconds) */
 } toe_pcg_stats;
 
 typedef struct toe_timings {  /* device seconds of the last call of each stage (CUDA events) */

@@ -74,3 +74,8 @@ def test_pipelined_matrix_free_operator(ctx, pkg):
 def test_boundary_selection_and_surface_traction(pkg, fo, golden_c1):
     import surface_checks as sc
     sc.check_surface(pkg, fo, golden_c1)
+
+
+def test_two_level_preconditioner(ctx, pkg, fo):
+    import two_level_checks as tc
+    tc.check_two_level(pkg, fo, ctx, [((12, 4, 2), False, (4, 2, 1), False), ((10, 4, 3), False, (3, 2, 2), True), ((8, 3, 2), True, (4, 1, 1), False)])

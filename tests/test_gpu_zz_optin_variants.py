@@ -31,3 +31,31 @@ def test_boundary_selection_and_surface_traction(pkg, fo, golden_c1):
     traction — against the oracle's literal restatement of SelectNodesForBC.jl / SurfaceTraction.jl."""
     import surface_checks as sc
     sc.check_surface(pkg, fo, golden_c1)
+
+
+def test_two_level_preconditioner(pkg, fo):
+    """Jacobi + rigid-body coarse space — same solution, far fewer iterations, matches its numpy
+    restatement; then the 1M-tet cantilever with the automatic 512 boxes."""
+    import json
+    import os
+    import two_level_checks as tc
+    ctx = pkg.Context(0)
+    try:
+        tc.check_two_level(pkg, fo, ctx, [((24, 8, 4), False, (8, 2, 1), False), ((24, 8, 4), False, (6, 3, 2), True), ((12, 4, 3), True, (4, 2, 1), False)])
+        dims = pkg.meshgen.SIZES["C3_1M"]
+        pts, cells = pkg.meshgen.cantilever(*dims)
+        ctx.set_mesh(pts, cells); ctx.build_dofs(); ctx.build_pattern()
+        ctx.assemble_lame(*pkg.create_material_model(1.0, 0.3))
+        import numpy as np
+        fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0); load = pkg.meshgen.nodes_at_plane(pts, 0, 60.0)
+        nfd = ctx.node_dofs(); pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
+        ctx.add_nodal_force(load, [0.0, 0.0, -1.0]); ctx.apply_dirichlet(pres)
+        sj = ctx.solve_pcg(1e-8, 1e-8, 40000); ej, _, _ = ctx.energy()
+        st = ctx.solve_pcg(1e-8, 1e-8, 40000, two_level=True); et, _, _ = ctx.energy()
+        print("1M tets: Jacobi %d iterations %.3f s | two-level (%d coarse dofs) %d iterations %.3f s (of which %.3f s coarse operator)"
+              % (sj["niter"], sj["solve_seconds"], st["coarse_dofs"], st["niter"], st["solve_seconds"], st["precond_seconds"]))
+        assert st["converged"] == 1 and st["coarse_dofs"] == 3072 and st["niter"] * 5 < sj["niter"] and abs(et - ej) <= 1e-6 * ej
+        g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_c3.json")))["C3_1M"]
+        assert abs(et - g["energy"]) <= 1e-6 * g["energy"]
+    finally:
+        ctx.close()

@@ -376,8 +376,9 @@ class SolverConfig:
             self.max_iterations = 10000
         if self.method not in ("auto", "cg", "direct"):
             raise TopOptError("method :%s is not on the GPU path (SPD system: :cg only)" % self.method)
-        if self.preconditioner != "diagonal":
-            raise TopOptError("preconditioner :%s is not on the GPU path (Jacobi only)" % self.preconditioner)
+        if self.preconditioner not in ("diagonal", "two_level"):
+            raise TopOptError("preconditioner :%s is not on the GPU path (:diagonal = Jacobi as in RobustSolver.jl:231-236, or "
+                              ":two_level = Jacobi + rigid-body coarse space)" % self.preconditioner)
 
 
 class StressField:
@@ -413,13 +414,13 @@ class StressField:
 DIRECT_EQUIVALENT_TOL = 1e-10
 
 
-def _solve(dh, constraints, tol, itmax, matrix_free, verbose, history=False):
+def _solve(dh, constraints, tol, itmax, matrix_free, verbose, history=False, two_level=False):
     ctx = dh.ctx
     for ch in constraints:                              # SINGLE APPLICATION POINT (:540-542)
         ctx.apply_dirichlet(ch.prescribed_dofs)
     if verbose:
         print("Solving linear system...")
-    st = ctx.solve_pcg(tol, tol, itmax, matrix_free=matrix_free, history=history)
+    st = ctx.solve_pcg(tol, tol, itmax, matrix_free=matrix_free, history=history, two_level=two_level)
     if st["breakdown"]:
         raise TopOptError("CG breakdown: p'Ap <= 0 (matrix not positive definite)")
     if not st["converged"] and verbose:
@@ -445,9 +446,10 @@ def solve_system_simp(K, f, dh, cellvalues, material_model, density_data, *const
 
 def solve_system_robust(K, f, dh, cellvalues, lam, mu, *constraints, config: SolverConfig | None = None):
     config = config or SolverConfig()
+    tl = config.preconditioner == "two_level"
     if config.method == "direct":
-        return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ctx.ndofs), config.matrix_free, config.verbose)
-    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, config.history)
+        return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ctx.ndofs), config.matrix_free, config.verbose, two_level=tl)
+    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, config.history, two_level=tl)
 
 
 def solve_system_robust_simp(K, f, dh, cellvalues, material_model, density_data, *constraints, config: SolverConfig | None = None):

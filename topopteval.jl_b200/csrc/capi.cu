@@ -93,6 +93,7 @@ void toe_destroy(toe_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     dist_destroy(ctx);
+    tl_destroy(ctx);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->cgs_host) cudaFreeHost(ctx->cgs_host);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

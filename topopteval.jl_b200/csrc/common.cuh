@@ -75,6 +75,7 @@ struct CGScalars {
 };
 
 struct DistState;   // dist.cu
+struct TwoLevel;    // twolevel.cu
 
 struct toe_ctx {
     int device = 0;
@@ -148,6 +149,7 @@ struct toe_ctx {
     CGScalars* cgs_host = nullptr;   // pinned readback buffer
 
     DistState* dist = nullptr;
+    TwoLevel* tl = nullptr;       // two-level preconditioner state (twolevel.cu), built on first use
     // views set by the multi-GPU layer (null / 0 on a single GPU)
     const unsigned char* owned = nullptr;   // per local dof-node: 1 if this rank owns it (masked reductions, Dirichlet diagonal)
     const int* glob2loc = nullptr;          // global dof-node id -> local id, -1 if not on this rank
@@ -283,3 +285,9 @@ int mesh_build_tiles(toe_ctx* ctx);
 int ebe_tile_launch(toe_ctx* ctx, const double* x, double* y, CGScalars* cg, bool mask, const int* done_flag, double* dot_out);
 int dist_sum_per_element(toe_ctx* ctx, const double* local_dev, double* global_host);   // per-cell output, global cell order
 void dist_destroy(toe_ctx* ctx);
+// two-level preconditioner (twolevel.cu)
+int tl_prepare(toe_ctx* ctx, int matrix_free, int* coarse_dofs, double* setup_seconds);
+int tl_cg_init(toe_ctx* ctx, double atol, double rtol, i64 itmax, i64 hist_cap);
+int tl_cg_after_operator(toe_ctx* ctx, i64 hist_cap);
+void tl_invalidate(toe_ctx* ctx);
+void tl_destroy(toe_ctx* ctx);

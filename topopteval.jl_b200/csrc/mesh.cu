@@ -99,6 +99,7 @@ int mesh_upload(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, const 
         return toe_fail(ctx, TOE_ERR_ARG, "mesh too large for 32-bit device indices (nn=%lld, ne=%lld)", (long long)nn, (long long)ne);
     ctx->have_mesh = ctx->have_dofs = ctx->have_pattern = ctx->have_contrib = ctx->have_K = ctx->have_solution = false;
     ctx->have_tiles = false; ctx->have_surface = false;
+    tl_invalidate(ctx);
     ctx->have_diag = false; ctx->any_dirichlet = false;
     ctx->mat.mode = MAT_NONE;
     ctx->op_generation++;

@@ -524,8 +524,12 @@ static int cgcg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap,
     return TOE_OK;
 }
 
-static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap) {
+static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, bool two_level = false) {
     CGScalars* cg = ctx->cgs.p;
+    if (two_level) {
+        TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, cg, true));
+        return tl_cg_after_operator(ctx, hist_cap);
+    }
     {
         TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, cg, true));
         LAUNCH(ctx, k_cg_xr, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p,
@@ -552,13 +556,17 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     if (!ctx->cgs_host) CU(cudaMallocHost((void**)&ctx->cgs_host, sizeof(CGScalars)));
     i64 launches0 = ctx->launches;
     const bool dist = ctx->dist != nullptr;
-    const int per_iter = dist ? 4 : 3;
+    const bool two_level = (flags & TOE_PCG_TWO_LEVEL) != 0;
+    if (two_level && dist) return toe_fail(ctx, TOE_ERR_STATE, "solve: the two-level preconditioner is not available on a partitioned ctx yet");
+    const int per_iter = dist ? 4 : (two_level ? 6 : 3);
+    int coarse_dofs = 0; double precond_seconds = 0.0;
     int CG_BATCH = CG_BATCH_DEFAULT;
     if (const char* eb = getenv("TOE_CG_BATCH")) { int v = atoi(eb); if (v >= 2) CG_BATCH = v & ~1; }
 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, ctx->stream));
+    if (two_level) TRY(tl_prepare(ctx, matrix_free, &coarse_dofs, &precond_seconds));      // ZᵀKZ and its inverse: part of the solve time
     // Partitioned runs: a solve that ends in a CG breakdown is restarted from x0 = 0 (at most twice) and the number of restarts is
     // reported.  One such first solve was seen at N=2 / 10M tets on the NCCL transport (identical re-runs converge); the restart
     // keeps the result valid while the cause is open.  TOE_DIST_NO_RETRY=1 disables it.
@@ -568,7 +576,9 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
             ctx->have_diag = false;
             TRY(compute_diag(ctx));
         }
-        if (!dist) {
+        if (two_level) {
+            TRY(tl_cg_init(ctx, atol, rtol, itmax, hist_cap));
+        } else if (!dist) {
             LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
                    ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, (const unsigned char*)nullptr, (double*)nullptr);
         } else {
@@ -586,14 +596,14 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
 
         bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
         if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture stalled on this stack; direct launches for now
-        i64 key = (ctx->op_generation * 4 + matrix_free * 2 + 1) * 4096 + CG_BATCH;
+        i64 key = (ctx->op_generation * 8 + (two_level ? 4 : 0) + matrix_free * 2 + 1) * 4096 + CG_BATCH;
         if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
             if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
             cudaGraph_t g = nullptr;
             CU(cudaStreamBeginCapture(ctx->stream, dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
             i64 l0 = ctx->launches;
             int st = TOE_OK;
-            for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap);
+            for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level);
             ctx->launches = l0;
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
             if (st != TOE_OK) { if (g) cudaGraphDestroy(g); return st; }
@@ -606,7 +616,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
         for (i64 bt = 0; bt < max_batches; bt++) {
             if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += per_iter * CG_BATCH; }
-            else for (int k = 0; k < CG_BATCH; k++) TRY(dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap));
+            else for (int k = 0; k < CG_BATCH; k++) TRY(dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level));
             CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             if (ctx->cgs_host->done) break;
@@ -651,6 +661,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         stats->spmv_bytes = op_bytes(ctx, matrix_free);
         stats->kernel_launches = ctx->launches - launches0;
         stats->restarts = restarts;
+        stats->coarse_dofs = coarse_dofs; stats->precond_seconds = precond_seconds;
     }
     if (history && history_cap > 0) {
         i64 cnt = h.iter + 1 < history_cap ? h.iter + 1 : history_cap;

@@ -188,6 +188,7 @@ struct PcgStats
     niter::Int64; converged::Int32; breakdown::Int32
     res0_M::Float64; res_M::Float64; rel_res_l2::Float64
     solve_seconds::Float64; spmv_seconds::Float64; spmv_bytes::Float64; kernel_launches::Int64; restarts::Int64
+    coarse_dofs::Int64; precond_seconds::Float64
 end
 
 "Lazy stand-in for Dict{Int,Vector{SymmetricTensor}}: nothing leaves the GPU until indexed."
@@ -203,7 +204,7 @@ end
 
 const DIRECT_EQUIVALENT_TOL = 1e-10      # `K \ f` entry points run PCG to the accuracy the reference's direct solve reaches
 
-function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbose)
+function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbose, two_level = false)
     c = dh.ctx
     for ch in constraints                                  # SINGLE APPLICATION POINT (:540-542)
         m = Ref(0.0)
@@ -212,7 +213,7 @@ function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbos
     verbose && println("Solving linear system...")
     st = Ref{PcgStats}()
     check(c, ccall((:toe_solve_pcg, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Int64, Cint, Ref{PcgStats}, Ptr{Float64}, Int64),
-                   c.ptr, tol, tol, itmax, matrix_free ? 1 : 0, st, C_NULL, 0))
+                   c.ptr, tol, tol, itmax, (matrix_free ? 1 : 0) | (two_level ? 4 : 0), st, C_NULL, 0))      # TOE_PCG_MATRIX_FREE | TOE_PCG_TWO_LEVEL
     st[].breakdown != 0 && error("CG breakdown: p'Ap <= 0 (matrix not positive definite)")
     st[].converged == 0 && @warn "PCG did not converge in $(st[].niter) iterations (residual $(st[].res_M))"
     u = Vector{Float64}(undef, dh.ndofs)
@@ -233,9 +234,10 @@ solve_system(K, f, dh, cv, λ, μ, constraints...) = _solve(dh, constraints, DIR
 solve_system_simp(K, f, dh, cv, material_model, density_data, constraints...) = _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ndofs), false, true)
 function solve_system_robust(K, f, dh, cv, λ, μ, constraints...; config::SolverConfig = SolverConfig())
     config.method in (:auto, :cg, :direct) || error("method :$(config.method) is not on the GPU path (SPD system: :cg only)")
-    config.preconditioner == :diagonal || error("preconditioner :$(config.preconditioner) is not on the GPU path (Jacobi only)")
-    config.method == :direct && return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ndofs), config.matrix_free, config.verbose)
-    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose)
+    config.preconditioner in (:diagonal, :two_level) || error("preconditioner :$(config.preconditioner) is not on the GPU path (:diagonal or :two_level)")
+    tl = config.preconditioner == :two_level             # Jacobi + rigid-body coarse space (TOE_PCG_TWO_LEVEL)
+    config.method == :direct && return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ndofs), config.matrix_free, config.verbose, tl)
+    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, tl)
 end
 solve_system_robust_simp(K, f, dh, cv, material_model, density_data, constraints...; config::SolverConfig = SolverConfig()) =
     solve_system_robust(K, f, dh, cv, nothing, nothing, constraints...; config = config)
