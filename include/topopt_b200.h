@@ -45,7 +45,7 @@ typedef struct toe_ctx toe_ctx;
 #define TOE_PCG_NO_GRAPH      2   /* launch kernels directly instead of replaying a CUDA graph */
 #define TOE_PCG_TWO_LEVEL     4   /* preconditioner M⁻¹ = D⁻¹ + Z(ZᵀKZ)⁻¹Zᵀ instead of Jacobi: Z = rigid-body modes of the boxes of a
                                      coarse grid over the mesh (≤ 6144 coarse unknowns); same stopping rule on sqrt(r'Mr).
-                                     SolverConfig.preconditioner = :two_level in the shims; single GPU only for now */
+                                     SolverConfig.preconditioner = :two_level in the shims; works on partitioned contexts too */
 
 typedef struct toe_pcg_stats {
     int64_t niter;            /* Krylov.jl stats.niter */

@@ -31,7 +31,7 @@ def _problem(pkg, dims, simp):
     return pts, cells, rho, fixed, load
 
 
-def _run(pkg, ctx, prob, distributed, mf, tol=1e-10):
+def _run(pkg, ctx, prob, distributed, mf, tol=1e-10, two_level=False):
     pts, cells, rho, fixed, load = prob
     lam, mu = pkg.create_material_model(1.0, 0.3)
     ctx.set_mesh(pts, cells, distributed=distributed)
@@ -46,7 +46,7 @@ def _run(pkg, ctx, prob, distributed, mf, tol=1e-10):
     nfd = ctx.node_dofs()
     pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
     m = ctx.apply_dirichlet(pres)
-    st = ctx.solve_pcg(tol, tol, 20000, matrix_free=mf, graph=False)
+    st = ctx.solve_pcg(tol, tol, 20000, matrix_free=mf, graph=False, two_level=two_level)
     u = ctx.solution()
     e, c, ee = ctx.energy(per_element=True)
     _, vm, mx, arg = ctx.stresses(False, True)
@@ -54,7 +54,7 @@ def _run(pkg, ctx, prob, distributed, mf, tol=1e-10):
                 nfd=nfd, mx=mx, arg=arg, vm=vm, diag=ctx.diagonal())
 
 
-def _run_ranks(pkg, world, prob, mf, repeats=1, tol=1e-10):
+def _run_ranks(pkg, world, prob, mf, repeats=1, tol=1e-10, two_level=False):
     uid = pkg.Context.comm_unique_id()
     out = [None] * world
     err = [None] * world
@@ -65,7 +65,7 @@ def _run_ranks(pkg, world, prob, mf, repeats=1, tol=1e-10):
             ctx.comm_init(world, rank, uid)
             res = []
             for _ in range(repeats):
-                res.append(_run(pkg, ctx, prob, True, mf, tol))
+                res.append(_run(pkg, ctx, prob, True, mf, tol, two_level))
             res[-1]["part"] = ctx.partition()
             res[-1]["sizes"] = ctx.local_sizes()
             res[-1]["transport"] = ctx.comm_info()["transport"]
@@ -139,3 +139,26 @@ def test_peer_memory_exchange_protocol(emu, world, dims, monkeypatch):
             r = p2p[rk][rep]
             assert r["conv"] == 1 and r["restarts"] == 0
             assert r["it"] == nccl[rk][0]["it"] and np.array_equal(r["u"], nccl[rk][0]["u"]), (rk, rep, r["it"], nccl[rk][0]["it"])
+
+
+@pytest.mark.parametrize("world,dims,simp,mf", [(2, (12, 4, 2), False, False), (4, (16, 4, 2), True, False), (2, (10, 4, 3), False, True)])
+def test_two_level_preconditioner_on_partitions(emu, world, dims, simp, mf, monkeypatch):
+    """Jacobi + rigid-body coarse space on a partitioned ctx: per-box sums over OWNED nodes + allreduce, coarse operator probed
+    through the interface-summed operator; must reproduce the single-ctx two-level solve (same boxes, same iteration count ±1)."""
+    pkg, lib = emu
+    monkeypatch.setenv("TOE_TL_BOXES", "4,2,1")
+    prob = _problem(pkg, dims, simp)
+    single = pkg.Context(0)
+    ref_j = _run(pkg, single, prob, False, mf)
+    ref = _run(pkg, single, prob, False, mf, two_level=True)
+    single.close()
+    assert ref["conv"] == 1 and ref["it"] < ref_j["it"]
+    ranks = _run_ranks(pkg, world, prob, mf, repeats=2, two_level=True)
+    for rk in range(world):
+        first, r = ranks[rk][0], ranks[rk][-1]
+        assert r["conv"] == 1 and r["brk"] == 0 and r["restarts"] == 0
+        assert np.array_equal(r["u"], ranks[0][-1]["u"]) and np.array_equal(first["u"], r["u"]) and first["it"] == r["it"]
+        assert abs(r["it"] - ref["it"]) <= 1, (r["it"], ref["it"])
+        assert np.linalg.norm(r["u"] - ref["u"]) <= 1e-8 * np.linalg.norm(ref["u"])
+        assert np.linalg.norm(r["u"] - ref_j["u"]) <= 1e-8 * np.linalg.norm(ref_j["u"])
+        assert abs(r["e"] - ref["e"]) <= 1e-8 * abs(ref["e"])

@@ -527,7 +527,12 @@ static int cgcg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap,
 static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, bool two_level = false) {
     CGScalars* cg = ctx->cgs.p;
     if (two_level) {
-        TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, cg, true));
+        if (ctx->dist) {     // partitioned: the local p'Ap partial (all local rows: p is interface-consistent) rides with the interface sum
+            TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, cg, true, &cg->done, &cg->gd[0][0]));
+            TRY(dist_exchange_allreduce(ctx, ctx->Ap.p, &cg->gd[0][0], 1));
+        } else {
+            TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, cg, true));
+        }
         return tl_cg_after_operator(ctx, hist_cap);
     }
     {
@@ -557,8 +562,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     i64 launches0 = ctx->launches;
     const bool dist = ctx->dist != nullptr;
     const bool two_level = (flags & TOE_PCG_TWO_LEVEL) != 0;
-    if (two_level && dist) return toe_fail(ctx, TOE_ERR_STATE, "solve: the two-level preconditioner is not available on a partitioned ctx yet");
-    const int per_iter = dist ? 4 : (two_level ? 6 : 3);
+    const int per_iter = two_level ? 6 : (dist ? 4 : 3);
     int coarse_dofs = 0; double precond_seconds = 0.0;
     int CG_BATCH = CG_BATCH_DEFAULT;
     if (const char* eb = getenv("TOE_CG_BATCH")) { int v = atoi(eb); if (v >= 2) CG_BATCH = v & ~1; }
@@ -603,7 +607,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
             CU(cudaStreamBeginCapture(ctx->stream, dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
             i64 l0 = ctx->launches;
             int st = TOE_OK;
-            for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level);
+            for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = (dist && !two_level) ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level);
             ctx->launches = l0;
             cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
             if (st != TOE_OK) { if (g) cudaGraphDestroy(g); return st; }
@@ -616,7 +620,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
         for (i64 bt = 0; bt < max_batches; bt++) {
             if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += per_iter * CG_BATCH; }
-            else for (int k = 0; k < CG_BATCH; k++) TRY(dist ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level));
+            else for (int k = 0; k < CG_BATCH; k++) TRY((dist && !two_level) ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level));
             CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             if (ctx->cgs_host->done) break;

@@ -71,18 +71,20 @@ __global__ void k_tl_check_adjacent(const int* __restrict__ blk_ptr, const int* 
 
 // stable counting sort of the dof-nodes by box: chunk = 256 consecutive nodes
 static const int TL_CHUNK = 256;
-__global__ void __launch_bounds__(TL_CHUNK) k_tl_count(const int* __restrict__ agg, int nq, int nchunks, int* __restrict__ cnt /* [m][nchunks] */) {
+// partitioned runs: only the nodes this rank OWNS are listed, so that the per-box sums of all ranks add up to the global sums
+__global__ void __launch_bounds__(TL_CHUNK) k_tl_count(const int* __restrict__ agg, const unsigned char* __restrict__ owned, int nq, int nchunks,
+                                                       int* __restrict__ cnt /* [m][nchunks] */) {
     int q = blockIdx.x * TL_CHUNK + threadIdx.x;
-    if (q < nq) atomicAdd(&cnt[(size_t)agg[q] * nchunks + blockIdx.x], 1);
+    if (q < nq && (!owned || owned[q])) atomicAdd(&cnt[(size_t)agg[q] * nchunks + blockIdx.x], 1);
 }
-__global__ void __launch_bounds__(TL_CHUNK) k_tl_fill(const int* __restrict__ agg, int nq, int nchunks, const int* __restrict__ start /* scanned cnt */,
-                                                      int* __restrict__ agg_nodes) {
+__global__ void __launch_bounds__(TL_CHUNK) k_tl_fill(const int* __restrict__ agg, const unsigned char* __restrict__ owned, int nq, int nchunks,
+                                                      const int* __restrict__ start /* scanned cnt */, int* __restrict__ agg_nodes) {
     __shared__ int sa[TL_CHUNK];
     const int q = blockIdx.x * TL_CHUNK + threadIdx.x;
-    const int a = q < nq ? agg[q] : -1;
+    const int a = (q < nq && (!owned || owned[q])) ? agg[q] : -1;
     sa[threadIdx.x] = a;
     __syncthreads();
-    if (q >= nq) return;
+    if (a < 0) return;
     int rank = 0;
     for (int t = 0; t < (int)threadIdx.x; t++) rank += (sa[t] == a);
     agg_nodes[start[(size_t)a * nchunks + blockIdx.x] + rank] = q;
@@ -140,7 +142,8 @@ __global__ void __launch_bounds__(256) k_tl_gemv(const double* __restrict__ A, c
 __global__ void __launch_bounds__(256) k_tl_z(const double* __restrict__ Minv, const double* __restrict__ r, const int* __restrict__ agg,
                                               const double* __restrict__ xq, const double* __restrict__ y, const unsigned char* __restrict__ dflag, TLGeom g,
                                               double* __restrict__ z, int nq, CGScalars* cg, int init, double atol, double rtol, i64 itmax,
-                                              double* hist, i64 hist_cap, double* partials, unsigned int* counter) {
+                                              double* hist, i64 hist_cap, double* partials, unsigned int* counter,
+                                              const unsigned char* __restrict__ owned, double* local_out) {
     __shared__ double red[32];
     if (!init && cg->done) return;
     double s = 0.0;
@@ -156,12 +159,13 @@ __global__ void __launch_bounds__(256) k_tl_z(const double* __restrict__ Minv, c
             const double ri = r[dof];
             const double zi = Minv[dof] * ri + (dflag[dof] ? 0.0 : u[cc]);
             z[dof] = zi;
-            s += ri * zi;
+            if (!owned || owned[q]) s += ri * zi;
         }
     }
     s = block_sum(s, red);
     double tot;
     if (grid_sum_last_block(s, partials, counter, red, &tot)) {
+        if (local_out) { *local_out = tot; return; }          // partitioned: the caller allreduces and closes (k_tl_close)
         if (init) {
             cg->gamma = tot; cg->pAp = 0.0; cg->beta = 0.0;
             cg->res0 = sqrt(tot > 0.0 ? tot : 0.0);
@@ -202,6 +206,29 @@ __global__ void __launch_bounds__(256) k_tl_p(const double* __restrict__ z, doub
     const double beta = first ? 0.0 : cg->beta;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+
+// partitioned runs: the scalars come back from an allreduce; one thread closes what the last block closes on a single GPU
+__global__ void k_tl_set_pAp(CGScalars* cg, const double* pAp) {
+    if (threadIdx.x || blockIdx.x || cg->done) return;
+    cg_after_pAp(cg, *pAp);
+}
+__global__ void k_tl_close(CGScalars* cg, const double* gamma, int init, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (!init && cg->done) return;
+    const double tot = *gamma;
+    if (init) {
+        cg->gamma = tot; cg->pAp = 0.0; cg->beta = 0.0;
+        cg->res0 = sqrt(tot > 0.0 ? tot : 0.0);
+        cg->eps = atol + rtol * cg->res0;
+        cg->iter = 0; cg->itmax = itmax;
+        cg->converged = (cg->res0 <= cg->eps) ? 1 : 0;
+        cg->done = (cg->converged || itmax <= 0) ? 1 : 0;
+        cg->breakdown = 0;
+        if (hist_cap > 0) hist[0] = cg->res0;
+    } else {
+        cg_after_gamma(cg, tot, hist, hist_cap);
+    }
 }
 
 // probing vector of (colour, mode): v_i = P_i[:,mode] for nodes whose box has that colour, masked at prescribed dofs
@@ -328,10 +355,12 @@ static int tl_setup(toe_ctx* ctx) {
     if (t->have_setup) return TOE_OK;
     if (!ctx->have_pattern) return toe_fail(ctx, TOE_ERR_STATE, "two-level preconditioner: call setup_problem first");
     const int nq = ctx->nq;
-    // bounding box of the referenced nodes
+    // bounding box: of the referenced nodes — on a partitioned ctx of ALL nodes of the global mesh (every rank holds the global
+    // coordinate array), so that every rank lays the same box grid without talking to the others
     const int nb = 64;
     DevBuf<double> part; CU(part.alloc(6 * nb));
-    LAUNCH(ctx, k_tl_bbox, nb, 256, 0, (const double*)ctx->xq.p, nq, part.p);
+    if (ctx->dist) LAUNCH(ctx, k_tl_bbox, nb, 256, 0, (const double*)ctx->xyz.p, (int)ctx->nn, part.p);
+    else           LAUNCH(ctx, k_tl_bbox, nb, 256, 0, (const double*)ctx->xq.p, nq, part.p);
     std::vector<double> hp(6 * nb);
     CU(cudaMemcpyAsync(hp.data(), part.p, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -344,6 +373,7 @@ static int tl_setup(toe_ctx* ctx) {
     if (const char* e = getenv("TOE_TL_BOXES")) sscanf(e, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
     CU(t->agg.alloc(nq));
     DevBuf<int> bad; CU(bad.alloc(1));
+    DevBuf<double> badd; CU(badd.alloc(1));
     for (;; target /= 2) {
         int b[3] = {1, 1, 1};
         if (forced[0] > 0 && forced[1] > 0 && forced[2] > 0 && (i64)forced[0] * forced[1] * forced[2] <= 1024) { b[0] = forced[0]; b[1] = forced[1]; b[2] = forced[2]; forced[0] = 0; }
@@ -365,6 +395,14 @@ static int tl_setup(toe_ctx* ctx) {
         int hb = 0;
         CU(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->dist) {                                           // every rank must take the same decision
+            double v = hb ? 1.0 : 0.0;
+            CU(cudaMemcpyAsync(badd.p, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            TRY(dist_allreduce(ctx, badd.p, 1));
+            CU(cudaMemcpyAsync(&v, badd.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            hb = v > 0.0;
+        }
         if (!hb || t->m == 1) break;                               // boxes at least as wide as the cells: the 27 probing colours are valid
         if (target < 2) target = 2;
     }
@@ -373,13 +411,13 @@ static int tl_setup(toe_ctx* ctx) {
     const size_t ncnt = (size_t)t->m * nchunks;
     DevBuf<int> cnt; CU(cnt.alloc(ncnt + 1));
     CU(cudaMemsetAsync(cnt.p, 0, (ncnt + 1) * sizeof(int), ctx->stream));
-    LAUNCH(ctx, k_tl_count, nchunks, TL_CHUNK, 0, (const int*)t->agg.p, nq, nchunks, cnt.p);
+    LAUNCH(ctx, k_tl_count, nchunks, TL_CHUNK, 0, (const int*)t->agg.p, ctx->owned, nq, nchunks, cnt.p);
     i64 total = 0;
     TRY(scan_exclusive_i32(ctx, cnt.p, cnt.p, (i64)ncnt, &total));
-    if (total != nq) return toe_fail(ctx, TOE_ERR_STATE, "two-level preconditioner: box lists hold %lld of %d nodes", (long long)total, nq);
+    if (!ctx->dist && total != nq) return toe_fail(ctx, TOE_ERR_STATE, "two-level preconditioner: box lists hold %lld of %d nodes", (long long)total, nq);
     CU(t->agg_nodes.alloc(nq)); CU(t->agg_ptr.alloc(t->m + 1));
-    LAUNCH(ctx, k_tl_fill, nchunks, TL_CHUNK, 0, (const int*)t->agg.p, nq, nchunks, (const int*)cnt.p, t->agg_nodes.p);
-    LAUNCH(ctx, k_tl_box_ptr, div_up(t->m + 1, 256), 256, 0, (const int*)cnt.p, nchunks, t->m, nq, t->agg_ptr.p);
+    LAUNCH(ctx, k_tl_fill, nchunks, TL_CHUNK, 0, (const int*)t->agg.p, ctx->owned, nq, nchunks, (const int*)cnt.p, t->agg_nodes.p);
+    LAUNCH(ctx, k_tl_box_ptr, div_up(t->m + 1, 256), 256, 0, (const int*)cnt.p, nchunks, t->m, (int)total, t->agg_ptr.p);
     CU(t->A.alloc((size_t)t->nc * t->nc)); CU(t->w.alloc(t->nc + 8)); CU(t->y.alloc(t->nc + 8));
     const size_t n = 3 * (size_t)nq;
     CU(t->z.alloc(n)); CU(t->tv.alloc(n)); CU(t->ty.alloc(n));
@@ -404,6 +442,7 @@ static int tl_build_inverse(toe_ctx* ctx, int matrix_free) {
             TRY(op_apply(ctx, t->tv.p, t->ty.p, matrix_free, nullptr, true));
             LAUNCH(ctx, k_tl_restrict, m, TL_RT, 0, (const int*)t->agg_ptr.p, (const int*)t->agg_nodes.p, (const double*)ctx->xq.p, (const unsigned char*)ctx->dflag.p,
                    (const double*)t->ty.p, g, t->w.p, (const int*)nullptr);
+            TRY(dist_allreduce(ctx, t->w.p, nc));                 // partitioned: per-box sums of the owned nodes of every rank
             LAUNCH(ctx, k_tl_scatter, div_up(6 * m, 256), 256, 0, (const double*)t->w.p, g, cx, cy, cz, mode, t->A.p, m, nc);
         }
     LAUNCH(ctx, k_tl_symmetrise, div_up((i64)nc * nc, 256), 256, 0, t->A.p, nc);
@@ -428,7 +467,6 @@ static int tl_build_inverse(toe_ctx* ctx, int matrix_free) {
 }
 
 int tl_prepare(toe_ctx* ctx, int matrix_free, int* coarse_dofs, double* setup_seconds) {
-    if (ctx->dist) return toe_fail(ctx, TOE_ERR_STATE, "the two-level preconditioner is not available on a partitioned ctx yet");
     if (ctx->tl && ctx->tl->have_setup && (size_t)ctx->tl->z.n < 3 * (size_t)ctx->nq) ctx->tl->have_setup = false;
     TRY(tl_setup(ctx));
     ctx->tl->setup_seconds = 0.0;
@@ -450,10 +488,16 @@ int tl_cg_init(toe_ctx* ctx, double atol, double rtol, i64 itmax, i64 hist_cap) 
     LAUNCH(ctx, k_tl_init, tl_vec_grid(n), 256, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, n);
     LAUNCH(ctx, k_tl_restrict, t->m, TL_RT, 0, (const int*)t->agg_ptr.p, (const int*)t->agg_nodes.p, (const double*)ctx->xq.p, (const unsigned char*)ctx->dflag.p,
            (const double*)ctx->r.p, g, t->w.p, (const int*)nullptr);
+    TRY(dist_allreduce(ctx, t->w.p, t->nc));
     LAUNCH(ctx, k_tl_gemv, div_up(t->nc, 8), 256, 0, (const double*)t->A.p, (const double*)t->w.p, t->y.p, t->nc, (const int*)nullptr);
+    double* gscal = ctx->dist ? &ctx->cgs.p->gd[1][0] : nullptr;       // partitioned: local γ partial → allreduce → k_tl_close
     LAUNCH(ctx, k_tl_z, tl_vec_grid(ctx->nq), 256, 0, (const double*)ctx->Minv.p, (const double*)ctx->r.p, (const int*)t->agg.p, (const double*)ctx->xq.p,
            (const double*)t->y.p, (const unsigned char*)ctx->dflag.p, g, t->z.p, ctx->nq, ctx->cgs.p, 1, atol, rtol, itmax, ctx->hist.p, hist_cap,
-           ctx->partials.p, ctx->counters.p + 9);
+           ctx->partials.p, ctx->counters.p + 9, ctx->owned, gscal);
+    if (ctx->dist) {
+        TRY(dist_allreduce(ctx, gscal, 1));
+        LAUNCH(ctx, k_tl_close, 1, 32, 0, ctx->cgs.p, (const double*)gscal, 1, atol, rtol, itmax, ctx->hist.p, hist_cap);
+    }
     LAUNCH(ctx, k_tl_p, tl_vec_grid(n), 256, 0, (const double*)t->z.p, ctx->p.p, n, (const CGScalars*)ctx->cgs.p, 1);
     return TOE_OK;
 }
@@ -464,13 +508,20 @@ int tl_cg_after_operator(toe_ctx* ctx, i64 hist_cap) {
     const TLGeom g = tl_geom(t);
     const size_t n = 3 * (size_t)ctx->nq;
     CGScalars* cg = ctx->cgs.p;
+    if (ctx->dist) LAUNCH(ctx, k_tl_set_pAp, 1, 32, 0, cg, (const double*)&cg->gd[0][0]);      // p'Ap summed over the ranks by the caller's exchange
     LAUNCH(ctx, k_tl_xr, tl_vec_grid(n), 256, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, ctx->u.p, ctx->r.p, n, (const CGScalars*)cg);
     LAUNCH(ctx, k_tl_restrict, t->m, TL_RT, 0, (const int*)t->agg_ptr.p, (const int*)t->agg_nodes.p, (const double*)ctx->xq.p, (const unsigned char*)ctx->dflag.p,
            (const double*)ctx->r.p, g, t->w.p, (const int*)&cg->done);
+    TRY(dist_allreduce(ctx, t->w.p, t->nc));
     LAUNCH(ctx, k_tl_gemv, div_up(t->nc, 8), 256, 0, (const double*)t->A.p, (const double*)t->w.p, t->y.p, t->nc, (const int*)&cg->done);
+    double* gscal = ctx->dist ? &cg->gd[1][0] : nullptr;
     LAUNCH(ctx, k_tl_z, tl_vec_grid(ctx->nq), 256, 0, (const double*)ctx->Minv.p, (const double*)ctx->r.p, (const int*)t->agg.p, (const double*)ctx->xq.p,
            (const double*)t->y.p, (const unsigned char*)ctx->dflag.p, g, t->z.p, ctx->nq, cg, 0, 0.0, 0.0, (i64)0, ctx->hist.p, hist_cap,
-           ctx->partials.p, ctx->counters.p + 9);
+           ctx->partials.p, ctx->counters.p + 9, ctx->owned, gscal);
+    if (ctx->dist) {
+        TRY(dist_allreduce(ctx, gscal, 1));
+        LAUNCH(ctx, k_tl_close, 1, 32, 0, cg, (const double*)gscal, 0, 0.0, 0.0, (i64)0, ctx->hist.p, hist_cap);
+    }
     LAUNCH(ctx, k_tl_p, tl_vec_grid(n), 256, 0, (const double*)t->z.p, ctx->p.p, n, (const CGScalars*)cg, 0);
     return TOE_OK;
 }
