@@ -148,6 +148,10 @@ struct toe_ctx {
     i64 op_generation = 0;    // bumped whenever the operator (mesh, material, K, constraints) changes
     CGScalars* cgs_host = nullptr;   // pinned readback buffer
 
+    // cudaFuncSetAttribute is per device: the opt-in to large dynamic shared memory is remembered per ctx, not per process
+    bool spmv_attr_set = false;
+    size_t ebe_attr_smem[2] = {0, 0}, pipe_attr_smem[2] = {0, 0};
+
     DistState* dist = nullptr;
     TwoLevel* tl = nullptr;       // two-level preconditioner state (twolevel.cu), built on first use
     // views set by the multi-GPU layer (null / 0 on a single GPU)

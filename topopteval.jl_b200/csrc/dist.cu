@@ -486,16 +486,20 @@ static const int XCHG_CTAS = 32, XCHG_THREADS = 256;      // all co-resident (th
 static const int XCHG_CTAS = 4, XCHG_THREADS = 64;        // tests/cuda_emu: same protocol, fewer fibers
 #endif
 
-// software grid barrier on a monotonically increasing counter (every CTA adds 1 per barrier)
-__device__ __forceinline__ void xchg_grid_barrier(u64* ctr, u64 target) {
+// software grid barrier on a monotonically increasing counter (every CTA adds 1 per barrier).  Bounded: if the other CTAs do
+// not arrive within ≈3 s (they are not co-resident, or one of them is stuck) the error flag is raised and the kernel moves
+// on — a wrong exchange is reported by dist_check_exchange, a hung GPU could not be.
+__device__ __forceinline__ void xchg_grid_barrier(u64* ctr, u64 target, int* err_flag, int* done_flag) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(ctr, 1ULL);
+        const long long t0 = clock64();
         while (*reinterpret_cast<volatile u64*>(ctr) < target) {
 #ifdef TOE_EMU
             emu::yield();
 #endif
+            if (clock64() - t0 > 6000000000LL) { atomicExch(err_flag, 1); if (done_flag) atomicExch(done_flag, 1); break; }
         }
         __threadfence();
     }
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_xchg(char* const* __restrict__
         dst[0] = scal[0]; dst[1] = nscal > 1 ? scal[1] : 0.0;
     }
     __threadfence_system();
-    xchg_grid_barrier(gbar, base + gridDim.x);
+    xchg_grid_barrier(gbar, base + gridDim.x, err_flag, done_flag);
     // 2. publish the sequence number in every peer's flag word, 3. wait for every peer's
     if (blockIdx.x == 0) {
         if (tid < nranks && tid != me) {
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_xchg(char* const* __restrict__
         __syncthreads();
         __threadfence_system();
     }
-    xchg_grid_barrier(gbar, base + 2ULL * gridDim.x);
+    xchg_grid_barrier(gbar, base + 2ULL * gridDim.x, err_flag, done_flag);
     // 4. scalars in rank order (bit-identical on all ranks)
     if (blockIdx.x == 0 && tid == 0 && nscal > 0) {
         const double* sc = reinterpret_cast<const double*>(mine + MB_OFF_SCAL) + (size_t)par * 32 * 2;

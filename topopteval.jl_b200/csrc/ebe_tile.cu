@@ -526,7 +526,7 @@ int ebe_tile_launch(toe_ctx* ctx, const double* x, double* y, CGScalars* cg, boo
         const int mp = (ctx->tile_max_nodes + 7) & ~7;
         const PipeLayout L(mp);
         if (L.total <= 200 * 1024) {
-            static size_t pipe_attr[2] = {0, 0};
+            size_t* pipe_attr = ctx->pipe_attr_smem;
             if (L.total > 48 * 1024 && L.total > pipe_attr[npc == 8]) {
                 CU(cudaFuncSetAttribute(k_ebe_pipe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
                 CU(cudaFuncSetAttribute(k_ebe_pipe<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
@@ -547,7 +547,7 @@ int ebe_tile_launch(toe_ctx* ctx, const double* x, double* y, CGScalars* cg, boo
         }
     }
     size_t smem = (3 * (size_t)TILE_REFS + 6 * (size_t)ctx->tile_max_nodes) * sizeof(double) + (TILE_REFS + (size_t)ctx->tile_max_nodes + 8) * sizeof(unsigned short);
-    static size_t attr_smem[2] = {0, 0};
+    size_t* attr_smem = ctx->ebe_attr_smem;
     if (smem > 48 * 1024 && smem > attr_smem[npc == 8]) {
         CU(cudaFuncSetAttribute(k_ebe_tile<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU(cudaFuncSetAttribute(k_ebe_tile<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

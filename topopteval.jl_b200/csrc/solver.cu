@@ -300,11 +300,10 @@ static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, 
         if (R > SPMV_ROWS) R = SPMV_ROWS;
         int nchunks = (ctx->nq + R - 1) / R;
         unsigned grid = (unsigned)(nchunks < N_SM ? nchunks : N_SM);          // persistent: one CTA per SM
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!ctx->spmv_attr_set) {
             CU(cudaFuncSetAttribute(k_spmv_bsr_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_PSMEM));
             CU(cudaFuncSetAttribute(k_spmv_bsr_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_PSMEM));
-            attr_set = true;
+            ctx->spmv_attr_set = true;
         }
         if (cg) LAUNCH(ctx, k_spmv_bsr_pipe<true>, grid, SPMV_PTHREADS, SPMV_PSMEM, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const double*)ctx->val.p,
                        ctx->ldv, x, y, ctx->nq, R, done_flag, cg, ctx->partials.p, ctx->counters.p + 1, dot_out);
