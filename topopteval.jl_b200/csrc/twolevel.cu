@@ -319,6 +319,145 @@ __global__ void __launch_bounds__(256) k_gj_update(double* __restrict__ A, int n
     }
 }
 
+// ---- blocked Gauss–Jordan (32-wide pivot blocks): the same in-place inverse with 1/30 of the memory traffic -----------------
+//   step K:  Dinv = A_KK⁻¹ (in shared memory);  R = Dinv·A_K: (row panel, R_K = Dinv);  C = A_:K (column panel, saved);
+//            A_ij ← (j∈K ? 0 : A_ij) − C_i R_j for rows i∉K;  A_K: ← R
+static const int GJB = 32;
+
+// empty modes (boxes without free nodes: zero diagonal) are decoupled before the elimination starts
+__global__ void k_gjb_flag_empty(const double* __restrict__ A, int nc, const double* __restrict__ dmax, double thr, int* __restrict__ skip, int* __restrict__ nskipped) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nc) return;
+    const int e = !(A[(size_t)k * nc + k] > thr * (*dmax));
+    skip[k] = e;
+    if (e) atomicAdd(nskipped, 1);
+}
+__global__ void k_gjb_clear_empty(double* __restrict__ A, int nc, const int* __restrict__ skip) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nc * nc) return;
+    const int i = (int)(t / nc), j = (int)(t - (size_t)i * nc);
+    if (skip[i] || skip[j]) A[t] = (i == j) ? 1.0 : 0.0;
+}
+
+// inverse of the bs×bs diagonal block in shared memory; a pivot that has become tiny decouples its mode (flagged in skip[])
+__global__ void __launch_bounds__(256) k_gjb_diag(const double* __restrict__ A, int nc, int k0, int bs, const double* __restrict__ dmax, double thr,
+                                                  double* __restrict__ Dinv /* GJB×GJB */, int* __restrict__ skip, int* __restrict__ nskipped) {
+    __shared__ double D[GJB][GJB + 1];
+    __shared__ double cp[GJB], rp[GJB];
+    __shared__ int s_skip;
+    for (int t = threadIdx.x; t < GJB * GJB; t += blockDim.x) {
+        const int i = t / GJB, j = t - i * GJB;
+        D[i][j] = (i < bs && j < bs) ? A[(size_t)(k0 + i) * nc + k0 + j] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int p = 0; p < bs; p++) {
+        if (threadIdx.x == 0) {
+            const bool already = skip[k0 + p] != 0;
+            const bool tiny = !(D[p][p] > thr * (*dmax));
+            s_skip = (already || tiny) ? 1 : 0;
+            if (tiny && !already) { skip[k0 + p] = 1; atomicAdd(nskipped, 1); }
+        }
+        __syncthreads();
+        const bool sk = s_skip != 0;
+        const double piv = D[p][p];
+        if (threadIdx.x < GJB) {
+            const int j = threadIdx.x;
+            cp[j] = (j == p || sk) ? 0.0 : D[j][p];
+            rp[j] = sk ? (j == p ? 1.0 : 0.0) : (j == p ? 1.0 / piv : D[p][j] / piv);
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < GJB * GJB; t += blockDim.x) {
+            const int i = t / GJB, j = t - i * GJB;
+            if (i == p) D[i][j] = rp[j];
+            else {
+                const double base = (j == p) ? 0.0 : D[i][j];
+                D[i][j] = base - cp[i] * rp[j];
+            }
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < GJB * GJB; t += blockDim.x) { const int i = t / GJB, j = t - i * GJB; Dinv[t] = D[i][j]; }
+}
+
+// column panel C[i][q] = A[i][k0+q] (0 for decoupled modes), row panel R[p][j] = Σ_q Dinv[p][q] A[k0+q][j] (j∉K), R[p][k0+q] = Dinv[p][q]
+__global__ void __launch_bounds__(256) k_gjb_panels(const double* __restrict__ A, int nc, int k0, int bs, const double* __restrict__ Dinv,
+                                                    const int* __restrict__ skip, double* __restrict__ C, double* __restrict__ R) {
+    __shared__ double Ds[GJB][GJB + 1];
+    for (int t = threadIdx.x; t < GJB * GJB; t += blockDim.x) Ds[t / GJB][t % GJB] = Dinv[t];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;          // one column of R and one row of C per thread
+    if (j >= nc) return;
+    for (int q = 0; q < GJB; q++) C[(size_t)j * GJB + q] = (q < bs && !skip[k0 + q]) ? A[(size_t)j * nc + k0 + q] : 0.0;
+    const bool inK = j >= k0 && j < k0 + bs;
+    double a[GJB];
+#pragma unroll
+    for (int q = 0; q < GJB; q++) a[q] = (q < bs && !inK) ? A[(size_t)(k0 + q) * nc + j] : 0.0;
+    for (int p = 0; p < GJB; p++) {
+        double v = 0.0;
+        if (p < bs) {
+            if (inK) v = Ds[p][j - k0];
+            else if (!skip[k0 + p]) {
+#pragma unroll
+                for (int q = 0; q < GJB; q++) v += Ds[p][q] * a[q];
+            }
+        }
+        R[(size_t)p * nc + j] = v;
+    }
+}
+
+// A_ij ← (j∈K ? 0 : A_ij) − Σ_q C[i][q] R[q][j]  for rows i∉K; 64×64 tile per CTA, 4×4 outputs per thread
+__global__ void __launch_bounds__(256) k_gjb_update(double* __restrict__ A, int nc, int k0, int bs, const double* __restrict__ C, const double* __restrict__ R, int tiles) {
+    __shared__ double Cs[64][GJB + 1];
+    __shared__ double Rs[GJB][64 + 2];
+    const int ti = blockIdx.x / tiles, tj = blockIdx.x - ti * tiles;
+    const int i0 = ti * 64, j0 = tj * 64;
+    for (int t = threadIdx.x; t < 64 * GJB; t += blockDim.x) {
+        const int r = t / GJB, q = t - r * GJB;
+        Cs[r][q] = (i0 + r < nc) ? C[(size_t)(i0 + r) * GJB + q] : 0.0;
+    }
+    for (int t = threadIdx.x; t < GJB * 64; t += blockDim.x) {
+        const int q = t / 64, c = t - q * 64;
+        Rs[q][c] = (j0 + c < nc) ? R[(size_t)q * nc + j0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+    for (int q = 0; q < GJB; q++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) a[u] = Cs[ty * 4 + u][q];
+#pragma unroll
+        for (int v = 0; v < 4; v++) b[v] = Rs[q][tx * 4 + v];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[u][v] += a[u] * b[v];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int i = i0 + ty * 4 + u;
+        if (i >= nc || (i >= k0 && i < k0 + bs)) continue;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const int j = j0 + tx * 4 + v;
+            if (j >= nc) continue;
+            const size_t at = (size_t)i * nc + j;
+            const double base = (j >= k0 && j < k0 + bs) ? 0.0 : A[at];
+            A[at] = base - acc[u][v];
+        }
+    }
+}
+__global__ void k_gjb_write_rows(double* __restrict__ A, int nc, int k0, int bs, const double* __restrict__ R) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)bs * nc) return;
+    const int p = (int)(t / nc), j = (int)(t - (size_t)p * nc);
+    A[(size_t)(k0 + p) * nc + j] = R[(size_t)p * nc + j];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
@@ -448,12 +587,29 @@ static int tl_build_inverse(toe_ctx* ctx, int matrix_free) {
     LAUNCH(ctx, k_tl_symmetrise, div_up((i64)nc * nc, 256), 256, 0, t->A.p, nc);
     double* dmax = t->y.p + nc;                       // scratch behind y
     LAUNCH(ctx, k_tl_diag_scale, 1, 256, 0, (const double*)t->A.p, nc, dmax);
-    DevBuf<double> colk; CU(colk.alloc(nc));
     DevBuf<int> skipped; CU(skipped.alloc(1));
     CU(cudaMemsetAsync(skipped.p, 0, sizeof(int), ctx->stream));
-    for (int k = 0; k < nc; k++) {
-        LAUNCH(ctx, k_gj_row, 1, 256, 0, t->A.p, nc, k, (const double*)dmax, 1e-13, colk.p, skipped.p);
-        LAUNCH(ctx, k_gj_update, nc, 256, 0, t->A.p, nc, k, (const double*)colk.p);
+    if (getenv("TOE_TL_GJ_UNBLOCKED")) {                     // reference form: one pivot per step (kept for cross-checks)
+        DevBuf<double> colk; CU(colk.alloc(nc));
+        for (int k = 0; k < nc; k++) {
+            LAUNCH(ctx, k_gj_row, 1, 256, 0, t->A.p, nc, k, (const double*)dmax, 1e-13, colk.p, skipped.p);
+            LAUNCH(ctx, k_gj_update, nc, 256, 0, t->A.p, nc, k, (const double*)colk.p);
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+    } else {
+        DevBuf<int> skip; CU(skip.alloc(nc));
+        DevBuf<double> Dinv, Cp, Rp; CU(Dinv.alloc(GJB * GJB)); CU(Cp.alloc((size_t)nc * GJB)); CU(Rp.alloc((size_t)GJB * nc));
+        LAUNCH(ctx, k_gjb_flag_empty, div_up(nc, 256), 256, 0, (const double*)t->A.p, nc, (const double*)dmax, 1e-13, skip.p, skipped.p);
+        LAUNCH(ctx, k_gjb_clear_empty, div_up((i64)nc * nc, 256), 256, 0, t->A.p, nc, (const int*)skip.p);
+        const int tiles = (nc + 63) / 64;
+        for (int k0 = 0; k0 < nc; k0 += GJB) {
+            const int bs = nc - k0 < GJB ? nc - k0 : GJB;
+            LAUNCH(ctx, k_gjb_diag, 1, 256, 0, (const double*)t->A.p, nc, k0, bs, (const double*)dmax, 1e-13, Dinv.p, skip.p, skipped.p);
+            LAUNCH(ctx, k_gjb_panels, div_up(nc, 256), 256, 0, (const double*)t->A.p, nc, k0, bs, (const double*)Dinv.p, (const int*)skip.p, Cp.p, Rp.p);
+            LAUNCH(ctx, k_gjb_update, tiles * tiles, 256, 0, t->A.p, nc, k0, bs, (const double*)Cp.p, (const double*)Rp.p, tiles);
+            LAUNCH(ctx, k_gjb_write_rows, div_up((i64)bs * nc, 256), 256, 0, t->A.p, nc, k0, bs, (const double*)Rp.p);
+        }
+        CU(cudaStreamSynchronize(ctx->stream));               // the panels go out of scope
     }
     LAUNCH(ctx, k_tl_symmetrise, div_up((i64)nc * nc, 256), 256, 0, t->A.p, nc);
     CU(cudaEventRecord(b, ctx->stream));
