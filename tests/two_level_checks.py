@@ -77,6 +77,19 @@ def check_two_level(pkg, fo, ctx, cases, tol=1e-10):
                     assert res.size == s1["niter"] + 1 and res[-1] <= tol + tol * res[0]
                     runs.append((s1["niter"], u1))
                 assert runs[0][0] == runs[1][0] and np.array_equal(runs[0][1], runs[1][1])          # graph replay = direct launches, bit for bit
+                if not mf:      # assembled K: the coarse operator comes straight from the blocks; the probing path must agree with it
+                    os.environ["TOE_TL_PROBE"] = "1"
+                    try:
+                        if simp:
+                            ctx.assemble_simp(1.0, 0.3, 1e-8, 3.0, rho)
+                        else:
+                            ctx.assemble_lame(lam, mu)
+                        ctx.add_nodal_force(load, [0.0, 0.0, -1.0]); ctx.apply_dirichlet(pres)
+                        sp_ = ctx.solve_pcg(tol, tol, 100000, two_level=True)
+                        assert sp_["converged"] == 1 and abs(sp_["niter"] - runs[0][0]) <= 2
+                        assert np.linalg.norm(ctx.solution() - runs[0][1]) <= 1e-8 * np.linalg.norm(runs[0][1])
+                    finally:
+                        os.environ.pop("TOE_TL_PROBE", None)
                 e, c, _ = ctx.energy()
                 assert abs(c - 2.0 * e) <= 1e-6 * c
                 if ref is not None:

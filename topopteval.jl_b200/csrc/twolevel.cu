@@ -266,6 +266,75 @@ __global__ void k_tl_scatter(const double* __restrict__ w, TLGeom g, int cx, int
     A[(size_t)t * nc + 6 * J + mode] = w[t];
 }
 
+// A_c(I,J) = Σ_{i∈I} Σ_{j∈J} P_iᵀ K_ij P_j straight from the assembled blocks (single GPU, assembled K): one CTA per (box I,
+// neighbour slot), threads stride over the nodes of I in list order, 36 partial sums each, fixed-order block reduction.
+// Replaces the ≤162 probing operator applications when K is in memory; the probing path stays for the matrix-free
+// operator and for partitioned runs.
+__device__ __forceinline__ void tl_mode(int b, const double d[3], double u[3]) {      // displacement of rigid-body mode b at offset d
+    u[0] = u[1] = u[2] = 0.0;
+    if (b < 3) u[b] = 1.0;
+    else if (b == 3) { u[1] = -d[2]; u[2] = d[1]; }
+    else if (b == 4) { u[0] = d[2]; u[2] = -d[0]; }
+    else { u[0] = -d[1]; u[1] = d[0]; }
+}
+__global__ void __launch_bounds__(128) k_tl_coarse_direct(const int* __restrict__ agg_ptr, const int* __restrict__ agg_nodes, const int* __restrict__ agg,
+                                                          const int* __restrict__ blk_ptr, const int* __restrict__ blk_col, const double* __restrict__ val, i64 ldv,
+                                                          const double* __restrict__ xq, const unsigned char* __restrict__ dflag, TLGeom g,
+                                                          double* __restrict__ A, int nc) {
+    __shared__ double red[32];
+    const int I = blockIdx.x / 27, slot = blockIdx.x - 27 * I;
+    const int ix = I % g.b[0], iy = (I / g.b[0]) % g.b[1], iz = I / (g.b[0] * g.b[1]);
+    const int jx = ix + slot % 3 - 1, jy = iy + (slot / 3) % 3 - 1, jz = iz + slot / 9 - 1;
+    if (jx < 0 || jx >= g.b[0] || jy < 0 || jy >= g.b[1] || jz < 0 || jz >= g.b[2]) return;     // uniform per CTA
+    const int J = jx + g.b[0] * (jy + g.b[1] * jz);
+    double cI[3], cJ[3]; tl_centre(g, I, cI); tl_centre(g, J, cJ);
+    double acc[36];
+#pragma unroll
+    for (int k = 0; k < 36; k++) acc[k] = 0.0;
+    for (int k = agg_ptr[I] + threadIdx.x; k < agg_ptr[I + 1]; k += blockDim.x) {
+        const int i = agg_nodes[k];
+        double di[3], mi[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { di[c] = xq[3 * (size_t)i + c] - cI[c]; mi[c] = dflag[3 * (size_t)i + c] ? 0.0 : 1.0; }
+        double T[3][6];                                        // Σ_{j∈J} K_ij P_j  (rows of prescribed dofs of i are dropped below)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int b = 0; b < 6; b++) T[c][b] = 0.0;
+        bool any = false;
+        for (int s = blk_ptr[i]; s < blk_ptr[i + 1]; s++) {
+            const int j = blk_col[s];
+            if (agg[j] != J) continue;
+            any = true;
+            double B[3][3], dj[3], mj[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                dj[c] = xq[3 * (size_t)j + c] - cJ[c]; mj[c] = dflag[3 * (size_t)j + c] ? 0.0 : 1.0;
+#pragma unroll
+                for (int d = 0; d < 3; d++) B[c][d] = val[(size_t)(3 * c + d) * ldv + s];
+            }
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+                double u[3]; tl_mode(b, dj, u);
+#pragma unroll
+                for (int c = 0; c < 3; c++) T[c][b] += B[c][0] * (mj[0] * u[0]) + B[c][1] * (mj[1] * u[1]) + B[c][2] * (mj[2] * u[2]);
+            }
+        }
+        if (!any) continue;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double u[3]; tl_mode(a, di, u);
+#pragma unroll
+            for (int b = 0; b < 6; b++) acc[6 * a + b] += (mi[0] * u[0]) * T[0][b] + (mi[1] * u[1]) * T[1][b] + (mi[2] * u[2]) * T[2][b];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 36; k++) {
+        const double v = block_sum(acc[k], red);
+        if (threadIdx.x == 0) A[(size_t)(6 * I + k / 6) * nc + 6 * J + k % 6] = v;
+    }
+}
+
 // A := (A + Aᵀ)/2; empty modes (zero diagonal: boxes without free nodes) are decoupled with a unit diagonal
 __global__ void k_tl_symmetrise(double* __restrict__ A, int nc) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -575,7 +644,11 @@ static int tl_build_inverse(toe_ctx* ctx, int matrix_free) {
     CU(cudaEventRecord(a, ctx->stream));
     CU(cudaMemsetAsync(t->A.p, 0, (size_t)nc * nc * sizeof(double), ctx->stream));
     const int ncx = t->b[0] < 3 ? t->b[0] : 3, ncy = t->b[1] < 3 ? t->b[1] : 3, ncz = t->b[2] < 3 ? t->b[2] : 3;
-    for (int cz = 0; cz < ncz; cz++) for (int cy = 0; cy < ncy; cy++) for (int cx = 0; cx < ncx; cx++)
+    const bool direct = !matrix_free && ctx->have_K && !ctx->dist && !getenv("TOE_TL_PROBE");
+    if (direct)
+        LAUNCH(ctx, k_tl_coarse_direct, 27 * m, 128, 0, (const int*)t->agg_ptr.p, (const int*)t->agg_nodes.p, (const int*)t->agg.p, (const int*)ctx->blk_ptr.p,
+               (const int*)ctx->blk_col.p, (const double*)ctx->val.p, ctx->ldv, (const double*)ctx->xq.p, (const unsigned char*)ctx->dflag.p, g, t->A.p, nc);
+    else for (int cz = 0; cz < ncz; cz++) for (int cy = 0; cy < ncy; cy++) for (int cx = 0; cx < ncx; cx++)
         for (int mode = 0; mode < 6; mode++) {
             LAUNCH(ctx, k_tl_probe, div_up(nq, 256), 256, 0, (const int*)t->agg.p, (const double*)ctx->xq.p, (const unsigned char*)ctx->dflag.p, g, cx, cy, cz, mode, t->tv.p, nq);
             TRY(op_apply(ctx, t->tv.p, t->ty.p, matrix_free, nullptr, true));
