@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include <chrono>
+#include <algorithm>
 
 #if !defined(__x86_64__)
 #error "the fiber switch below is written for x86-64 (System V ABI)"
@@ -172,9 +173,18 @@ void run_block(Rank& r, unsigned b, unsigned T, size_t smem) {
     for (unsigned t = 0; t < T; t++) fiber_prepare(r, (int)t);
     unsigned remaining = T;
     unsigned long long idle_passes = 0;
+    // EMU_SHUFFLE=<seed>: threads of a block are resumed in a fresh pseudo-random order on every pass instead of 0,1,2,… — code
+    // that silently depends on the order in which threads happen to run (a missing barrier) then gives different answers
+    static const char* shuffle_env = getenv("EMU_SHUFFLE");
+    static thread_local std::vector<unsigned> order;
+    static thread_local unsigned long long rng = 0;
+    if (shuffle_env) { if (!rng) rng = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)atoll(shuffle_env); order.resize(T); for (unsigned t = 0; t < T; t++) order[t] = t; }
     while (remaining > 0) {
         unsigned long long p0 = r.progress;
-        for (unsigned t = 0; t < T; t++) {
+        if (shuffle_env)
+            for (unsigned t = T; t > 1; t--) { rng = rng * 6364136223846793005ULL + 1442695040888963407ULL; unsigned j = (unsigned)((rng >> 33) % t); std::swap(order[t - 1], order[j]); }
+        for (unsigned tt = 0; tt < T; tt++) {
+            const unsigned t = shuffle_env ? order[tt] : tt;
             Fiber& f = r.fibers[t];
             if (f.done) continue;
             r.cur = (int)t; threadIdx.x = t;
