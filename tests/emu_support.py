@@ -25,6 +25,8 @@ def build_emu(extra: str = "", opt: str = "-O2") -> str:
 
 
 def load_emu():
+    # threads of a block are resumed in a pseudo-random order (fixed seed): stricter than 0,1,2,… and still reproducible
+    os.environ.setdefault("EMU_SHUFFLE", "20261018")
     build_emu()
     import __graft_entry__ as graft
     pkg = graft.load_package()
