@@ -206,6 +206,16 @@ struct StageTimer {
     }
 };
 
+// a pair of events that is destroyed on every exit path (error returns included)
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() {}
+    EventPair(const EventPair&) = delete;
+    EventPair& operator=(const EventPair&) = delete;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    cudaError_t create() { cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
+};
+
 // ---- device reductions ---------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

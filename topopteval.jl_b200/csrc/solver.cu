@@ -566,8 +566,8 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     int CG_BATCH = CG_BATCH_DEFAULT;
     if (const char* eb = getenv("TOE_CG_BATCH")) { int v = atoi(eb); if (v >= 2) CG_BATCH = v & ~1; }
 
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    EventPair ev; CU(ev.create());
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     CU(cudaEventRecord(e0, ctx->stream));
     if (two_level) TRY(tl_prepare(ctx, matrix_free, &coarse_dofs, &precond_seconds));      // ZᵀKZ and its inverse: part of the solve time
     // Partitioned runs: a solve that ends in a CG breakdown is restarted from x0 = 0 (at most twice) and the number of restarts is
@@ -629,7 +629,6 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaEventSynchronize(e1));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     CU(cudaGetLastError());
     CGScalars h = *ctx->cgs_host;
     ctx->tm.solve = ms * 1e-3;
@@ -652,14 +651,14 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         stats->rel_res_l2 = hn[1] > 0 ? sqrt(hn[0] / hn[1]) : sqrt(hn[0]);
         // operator time: a few isolated launches (local product only)
         const int reps = 5;
-        cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+        EventPair ev2; CU(ev2.create());
+        cudaEvent_t a = ev2.a, b = ev2.b;
         TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
         CU(cudaEventRecord(a, ctx->stream));
         for (int k = 0; k < reps; k++) TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
         CU(cudaEventRecord(b, ctx->stream));
         CU(cudaEventSynchronize(b));
         float oms = 0; cudaEventElapsedTime(&oms, a, b);
-        cudaEventDestroy(a); cudaEventDestroy(b);
         stats->spmv_seconds = (double)h.iter * (oms * 1e-3 / reps);
         stats->spmv_bytes = op_bytes(ctx, matrix_free);
         stats->kernel_launches = ctx->launches - launches0;
@@ -677,14 +676,14 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
 int time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out) {
     TRY(ensure_vectors(ctx));
     if (reps < 1) reps = 1;
-    cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    EventPair ev; CU(ev.create());
+    cudaEvent_t a = ev.a, b = ev.b;
     TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, false));
     CU(cudaEventRecord(a, ctx->stream));
     for (int k = 0; k < reps; k++) TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, false));
     CU(cudaEventRecord(b, ctx->stream));
     CU(cudaEventSynchronize(b));
     float ms = 0; cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a); cudaEventDestroy(b);
     CU(cudaGetLastError());
     if (seconds_out) *seconds_out = ms * 1e-3 / reps;
     if (bytes_out) *bytes_out = op_bytes(ctx, matrix_free);

@@ -640,7 +640,8 @@ static int tl_build_inverse(toe_ctx* ctx, int matrix_free) {
     if (t->built_generation == ctx->op_generation && t->built_matrix_free == matrix_free) return TOE_OK;
     const TLGeom g = tl_geom(t);
     const int nq = ctx->nq, nc = t->nc, m = t->m;
-    cudaEvent_t a, b; CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    EventPair ev; CU(ev.create());
+    cudaEvent_t a = ev.a, b = ev.b;
     CU(cudaEventRecord(a, ctx->stream));
     CU(cudaMemsetAsync(t->A.p, 0, (size_t)nc * nc * sizeof(double), ctx->stream));
     const int ncx = t->b[0] < 3 ? t->b[0] : 3, ncy = t->b[1] < 3 ? t->b[1] : 3, ncz = t->b[2] < 3 ? t->b[2] : 3;
@@ -688,7 +689,6 @@ static int tl_build_inverse(toe_ctx* ctx, int matrix_free) {
     CU(cudaEventRecord(b, ctx->stream));
     CU(cudaEventSynchronize(b));
     float ms = 0; cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a); cudaEventDestroy(b);
     CU(cudaGetLastError());
     t->setup_seconds = ms * 1e-3;
     t->built_generation = ctx->op_generation; t->built_matrix_free = matrix_free;
