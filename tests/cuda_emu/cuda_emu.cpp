@@ -215,9 +215,28 @@ void run_grid(Rank& r, unsigned grid, unsigned block, size_t smem, const std::fu
 }
 }  // namespace
 
+namespace {
+std::mutex g_attr_mutex;
+std::map<const void*, int> g_max_dyn_smem;
+}
+extern "C" void emu_set_max_dyn_smem(const void* fn, int bytes) { std::lock_guard<std::mutex> lk(g_attr_mutex); g_max_dyn_smem[fn] = bytes; }
+extern "C" void emu_misaligned(const void* p, unsigned bytes) {
+    fprintf(stderr, "cuda_emu: MISALIGNED %u-byte load at %p\n", bytes, p);
+    if (g_rank) g_rank->last_error = 716;
+}
+
 namespace emu {
-void launch(unsigned grid, unsigned block, size_t smem, std::function<void()> body) {
+void launch(unsigned grid, unsigned block, size_t smem, std::function<void()> body, const void* fn) {
     Rank& r = rank_state();
+    if (smem > 48 * 1024 && fn) {             // CUDA refuses more than 48 KB of dynamic shared memory unless the kernel opted in
+        std::lock_guard<std::mutex> lk(g_attr_mutex);
+        auto it = g_max_dyn_smem.find(fn);
+        if (it == g_max_dyn_smem.end() || (size_t)it->second < smem) {
+            fprintf(stderr, "cuda_emu: launch with %zu bytes of dynamic shared memory without cudaFuncSetAttribute(MaxDynamicSharedMemorySize)\n", smem);
+            r.last_error = cudaErrorInvalidValue;
+            return;
+        }
+    }
     if (grid == 0) { r.last_error = cudaErrorInvalidValue; return; }    // CUDA: invalid configuration
     if (r.capture) { r.capture->nodes.push_back(GraphNode{grid, block, smem, std::move(body)}); return; }
     run_grid(r, grid, block, smem, body);

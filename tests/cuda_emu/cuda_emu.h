@@ -98,11 +98,15 @@ cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
 cudaError_t cudaIpcCloseMemHandle(void* p);
 }
-template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+extern "C" void emu_set_max_dyn_smem(const void* fn, int bytes);
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F f, int attr, int value) {
+    if (attr == cudaFuncAttributeMaxDynamicSharedMemorySize) emu_set_max_dyn_smem(reinterpret_cast<const void*>(f), value);
+    return cudaSuccess;
+}
 
 // ---- kernel launch ---------------------------------------------------------------------------------------------------
 namespace emu {
-void launch(unsigned grid, unsigned block, size_t smem, std::function<void()> body);   // runs (or records, during capture) the grid
+void launch(unsigned grid, unsigned block, size_t smem, std::function<void()> body, const void* fn = nullptr);   // runs (or records, during capture) the grid
 void* dyn_smem();                          // dynamic shared memory of the running block
 void yield();                              // cooperative reschedule (used by spin loops)
 void cp_async(void* dst, const void* src, unsigned bytes);   // cp.async modelled at its LATEST legal completion: performed at the issuing thread's wait
@@ -120,7 +124,11 @@ static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline long long clock64() { return emu::clock(); }
-template <class T> static inline T __ldg(const T* p) { return *p; }
+extern "C" void emu_misaligned(const void* p, unsigned bytes);
+template <class T> static inline T __ldg(const T* p) {
+    if (sizeof(T) >= 8 && ((size_t)p % (sizeof(T) > 16 ? 16 : sizeof(T)))) emu_misaligned(p, (unsigned)sizeof(T));   // vector loads fault on a GPU when misaligned
+    return *p;
+}
 template <class T> static inline T __ldcg(const T* p) { return *p; }
 template <class T> static inline T __ldcv(const T* p) { return *(const volatile T*)p; }
 static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }

@@ -181,7 +181,8 @@ typedef unsigned smem_ptr_t;       // 32-bit shared-window address, as the mbarr
 // tests/cuda_emu (host-side logic check of these very sources, test infrastructure only): a launch runs the grid on fibers
 #define LAUNCH(ctx, kern, grid, block, smem, ...) do { \
     auto _args = std::make_tuple(__VA_ARGS__); \
-    emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [_args]() { std::apply([](auto... a) { kern(a...); }, _args); }); \
+    emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [_args]() { std::apply([](auto... a) { kern(a...); }, _args); }, \
+                reinterpret_cast<const void*>(&kern)); \
     (ctx)->launches++; } while (0)
 #define TOE_DYN_SMEM(type, name, align) type* name = reinterpret_cast<type*>(emu::dyn_smem())
 typedef size_t smem_ptr_t;
