@@ -1,52 +1,96 @@
-"""Opt-in kernel variants on a B200 (ROWS assembly, pipelined matrix-free operator).  The file name sorts last on purpose: these
-variants were written after the round-1 GPU budget was spent (logic verified on the emulated build) and are not defaults yet."""
-import pytest
+"""Opt-in kernel variants on a B200 (ROWS assembly, pipelined matrix-free operator, boundary selection / surface traction,
+two-level preconditioner).  The file name sorts last on purpose: these variants were written after the round-1 GPU budget was
+spent (logic verified on the emulated build) and are not defaults yet.
 
-import rows_variant_checks as rc
+Every test runs in a CHILD process with its own time limit: a kernel that has never met real hardware may fault (a CUDA
+context error is sticky for the whole process) or hang, and neither may take the remaining tests down with it."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
 
 pytestmark = pytest.mark.gpu
 
+TESTS = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(TESTS)
 
-def test_rows_variant(pkg, fo, golden_c1):
-    ctx = pkg.Context(0)
+PRELUDE = """
+import json, os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import __graft_entry__ as graft
+pkg = graft.load_package()
+from oracle import fea_oracle as fo
+golden_c1 = dict(np.load(os.path.join(%r, "golden", "c1_tet_beam.npz")))
+if os.environ.get("TOE_TEST_EMU") == "1":      # dry run of this file's plumbing where there is no GPU (tests/cuda_emu, test infrastructure)
+    import emu_support
+    pkg._lib._lib = emu_support.load_emu()[1]
+""" % (ROOT, TESTS, TESTS)
+
+
+def run_isolated(body, timeout):
+    code = PRELUDE + textwrap.dedent(body) + "\nprint('ISOLATED-OK')\n"
     try:
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired as ex:
+        out = (ex.stdout or b"")
+        out = out.decode(errors="replace") if isinstance(out, bytes) else out
+        raise AssertionError("child exceeded %d s (hang?)\n%s" % (timeout, out[-2000:]))
+    sys.stdout.write(r.stdout[-4000:])
+    assert r.returncode == 0 and "ISOLATED-OK" in r.stdout, "rc=%d\n%s\n%s" % (r.returncode, r.stdout[-3000:], r.stderr[-3000:])
+
+
+def test_rows_variant():
+    run_isolated("""
+        import rows_variant_checks as rc
+        ctx = pkg.Context(0)
         rc.check_rows_variant(pkg, fo, ctx, golden_c1)
-    finally:
         ctx.close()
+    """, 420)
 
 
-def test_pipelined_matrix_free_operator_equals_tile_kernel(pkg):
+def test_pipelined_matrix_free_operator_equals_tile_kernel():
     """221k tets = 864 tiles on ≤ 444 persistent CTAs (several tiles per CTA), plus a Hex8 mesh and a forced 37-CTA grid."""
-    import ebe_pipe_checks as pc
-    ctx = pkg.Context(0)
-    try:
+    run_isolated("""
+        import ebe_pipe_checks as pc
+        ctx = pkg.Context(0)
         pc.check_pipe_equals_tile(pkg, ctx, [((96, 32, 12), False), ((40, 16, 8), True)], grids=(None, 37), solve=False)
         pc.check_pipe_equals_tile(pkg, ctx, [((24, 8, 4), False)], grids=(None, 3), solve=True)
-    finally:
         ctx.close()
+    """, 420)
 
 
-def test_boundary_selection_and_surface_traction(pkg, fo, golden_c1):
+def test_boundary_selection_and_surface_traction():
     """SURVEY §8(f) next-row 3 on the GPU: surface extraction, plane / circle selection, facets, area, uniform and callback
     traction — against the oracle's literal restatement of SelectNodesForBC.jl / SurfaceTraction.jl."""
-    import surface_checks as sc
-    sc.check_surface(pkg, fo, golden_c1)
+    run_isolated("""
+        import surface_checks as sc
+        sc.check_surface(pkg, fo, golden_c1)
+    """, 420)
 
 
-def test_two_level_preconditioner(pkg, fo):
-    """Jacobi + rigid-body coarse space — same solution, far fewer iterations, matches its numpy
-    restatement; then the 1M-tet cantilever with the automatic 512 boxes."""
-    import json
-    import os
-    import two_level_checks as tc
-    ctx = pkg.Context(0)
-    try:
+def test_two_level_preconditioner_small_meshes():
+    """Jacobi + rigid-body coarse space — same solution as the oracle's direct solve, far fewer
+    iterations than Jacobi, iteration counts as in its numpy restatement."""
+    run_isolated("""
+        import two_level_checks as tc
+        ctx = pkg.Context(0)
         tc.check_two_level(pkg, fo, ctx, [((24, 8, 4), False, (8, 2, 1), False), ((24, 8, 4), False, (6, 3, 2), True), ((12, 4, 3), True, (4, 2, 1), False)])
+        ctx.close()
+    """, 600)
+
+
+def test_two_level_preconditioner_1m_tets():
+    """the 1M-tet cantilever with the automatic 512 boxes: same energy as the Jacobi solve and as the frozen oracle value; the
+    iteration count is compared with the numpy restatement of the same preconditioner on the C oracle's K (145)."""
+    run_isolated("""
+        ctx = pkg.Context(0)
         dims = pkg.meshgen.SIZES["C3_1M"]
         pts, cells = pkg.meshgen.cantilever(*dims)
         ctx.set_mesh(pts, cells); ctx.build_dofs(); ctx.build_pattern()
         ctx.assemble_lame(*pkg.create_material_model(1.0, 0.3))
-        import numpy as np
         fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0); load = pkg.meshgen.nodes_at_plane(pts, 0, 60.0)
         nfd = ctx.node_dofs(); pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
         ctx.add_nodal_force(load, [0.0, 0.0, -1.0]); ctx.apply_dirichlet(pres)
@@ -54,10 +98,14 @@ def test_two_level_preconditioner(pkg, fo):
         st = ctx.solve_pcg(1e-8, 1e-8, 40000, two_level=True); et, _, _ = ctx.energy()
         print("1M tets: Jacobi %d iterations %.3f s | two-level (%d coarse dofs) %d iterations %.3f s (of which %.3f s coarse operator)"
               % (sj["niter"], sj["solve_seconds"], st["coarse_dofs"], st["niter"], st["solve_seconds"], st["precond_seconds"]))
-        assert st["converged"] == 1 and st["coarse_dofs"] == 3072 and st["niter"] * 5 < sj["niter"] and abs(et - ej) <= 1e-6 * ej
-        g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_c3.json")))["C3_1M"]
-        assert abs(et - g["energy"]) <= 1e-6 * g["energy"]
-        k_ref = g["two_level"]["niter"]                     # numpy restatement of the same preconditioner on the C oracle's K: 145
-        assert abs(st["niter"] - k_ref) <= max(5, k_ref // 12), (st["niter"], k_ref)
-    finally:
+        assert sj["converged"] == 1 and st["converged"] == 1 and st["coarse_dofs"] == 3072
+        assert abs(et - ej) <= 1e-6 * ej, (et, ej)
+        g = json.load(open(os.path.join(os.getcwd(), "tests", "golden", "fullsize_c3.json")))["C3_1M"]
+        assert abs(et - g["energy"]) <= 1e-6 * g["energy"], (et, g["energy"])
+        assert st["niter"] * 5 < sj["niter"], (st["niter"], sj["niter"])
+        k_ref = g["two_level"]["niter"]
+        # reduction order differs between the GPU and numpy, so the count may move by a few iterations; a different ORDER OF
+        # MAGNITUDE would mean a different preconditioner
+        assert abs(st["niter"] - k_ref) <= max(10, k_ref // 5), (st["niter"], k_ref)
         ctx.close()
+    """, 600)
