@@ -173,6 +173,17 @@ int toe_energy_assembled(toe_ctx* ctx, double* half_uKu);
 /* sigma (may be NULL): 6 x nqp x ne doubles (xx,yy,zz,xy,yz,xz per quadrature point, nqp = 4 tet / 8 hex);
  * von_mises (may be NULL): ne doubles, von Mises of the qp-averaged stress; max + 1-based argmax (first max wins). */
 int toe_stresses(toe_ctx* ctx, double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell);
+/* The reference's free functions: calculate_stresses(u, dh, cellvalues, λ, μ) (FiniteElementAnalysis.jl:440) and
+ * calculate_stresses_simp(u, dh, cellvalues, material_model, density_data) (:730) take ANY displacement vector and material.
+ * u: n doubles in Ferrite dof order, or NULL = the solution stored in the ctx.  These calls read the mesh only: K, f, the
+ * constraints, the material and the stored solution of the ctx are left untouched.  Outputs as for toe_stresses. */
+int toe_calculate_stresses(toe_ctx* ctx, const double* u, double lambda, double mu,
+                           double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell);
+int toe_calculate_stresses_simp(toe_ctx* ctx, const double* u, double E0, double nu, double Emin, double p, const double* density,
+                                double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell);
+/* material_model given as an arbitrary callable: the shim evaluates it per cell on the host (as toe_assemble_lame_per_cell) */
+int toe_calculate_stresses_lame_per_cell(toe_ctx* ctx, const double* u, const double* lambda_e, const double* mu_e,
+                                         double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell);
 
 /* ---- operator hooks for tests and bench ----------------------------------------------------------- */
 /* y = K x with the current (possibly constrained) operator; matrix_free selects the EbE kernel. */

@@ -50,8 +50,15 @@ def _run(pkg, ctx, prob, distributed, mf, tol=1e-10, two_level=False):
     u = ctx.solution()
     e, c, ee = ctx.energy(per_element=True)
     _, vm, mx, arg = ctx.stresses(False, True)
+    # the free-function form: another field (global dof order on every rank), another material, ctx state untouched
+    w = np.cos(np.arange(u.size) * 0.37)
+    if rho is not None:
+        sg2, vm2, mx2, arg2 = ctx.calculate_stresses(w, simp=(2.0, 0.25, 1e-6, 2.0, rho), want_sigma=True, want_vm=True)
+    else:
+        sg2, vm2, mx2, arg2 = ctx.calculate_stresses(w, lame=(3.0, 1.5), want_sigma=True, want_vm=True)
+    assert np.array_equal(ctx.solution(), u)
     return dict(u=u, e=e, c=c, ee=ee, it=st["niter"], conv=st["converged"], brk=st["breakdown"], restarts=st["restarts"], m=m, f=ctx.rhs(),
-                nfd=nfd, mx=mx, arg=arg, vm=vm, diag=ctx.diagonal())
+                nfd=nfd, mx=mx, arg=arg, vm=vm, diag=ctx.diagonal(), sg2=sg2, vm2=vm2, mx2=mx2, arg2=arg2)
 
 
 def _run_ranks(pkg, world, prob, mf, repeats=1, tol=1e-10, two_level=False):
@@ -120,6 +127,8 @@ def test_partitioned_equals_single_ctx(emu, world, dims, simp, mf):
         assert abs(r["it"] - ref["it"]) <= max(5, ref["it"] // 50)
         assert r["arg"] == ref["arg"] and np.max(np.abs(r["vm"] - ref["vm"])) <= 1e-7 * ref["mx"]
         assert np.max(np.abs(r["spmv"] - y_single)) <= 1e-12 * np.max(np.abs(y_single))
+        # per-cell outputs of the free-function stress recovery: every cell is computed by exactly one rank with the single-ctx arithmetic
+        assert np.array_equal(r["sg2"], ref["sg2"]) and np.array_equal(r["vm2"], ref["vm2"]) and (r["mx2"], r["arg2"]) == (ref["mx2"], ref["arg2"])
 
 
 @pytest.mark.parametrize("world,dims", [(2, (12, 4, 2)), (4, (16, 4, 2)), (8, (24, 4, 2))])

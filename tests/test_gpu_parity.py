@@ -367,6 +367,63 @@ def test_stresses(ctx, pkg, fo, golden_c1, golden_c2):
         assert arg == argref == int(g["max_stress_cell"]) and abs(mx - float(g["max_von_mises"])) <= 1e-9 * mx
 
 
+def test_calculate_stresses_free_functions(ctx, pkg, fo, golden_c1, golden_c2):
+    """calculate_stresses(u, dh, cv, λ, μ) / calculate_stresses_simp(u, dh, cv, model, ρ) are free functions in the reference
+    (FiniteElementAnalysis.jl:440 / :730): any u, any material — and the ctx's own K, material and solution are not touched."""
+    def s6_of(sref):
+        return np.stack([sref[..., 0, 0], sref[..., 1, 1], sref[..., 2, 2], sref[..., 0, 1], sref[..., 1, 2], sref[..., 0, 2]], axis=-1)
+
+    # Tet4: the ctx holds K(λ₀, μ₀) and a stored field v; stresses are asked for another field under another material
+    g = golden_c1
+    pts, cells = g["points"], g["cells"].astype(np.int64)
+    _setup(ctx, pts, cells)
+    prob = fo.setup_problem(pts, cells)
+    lam0, mu0 = fo.create_material_model(1.0, 0.3)
+    ctx.assemble_lame(lam0, mu0)
+    vals0 = ctx.values()
+    v = np.random.default_rng(5).standard_normal(ctx.ndofs)
+    ctx.set_solution(v)
+    own = ctx.stresses(False, True)
+    lam1, mu1 = fo.create_material_model(210.0, 0.25)
+    sig, vm, mx, arg = ctx.calculate_stresses(g["u"], lame=(lam1, mu1), want_sigma=True, want_vm=True)
+    sref, vmref, mxref, argref = fo.calculate_stresses(prob, g["u"], lam1, mu1)
+    assert np.max(np.abs(sig - s6_of(sref))) <= 1e-10 * np.abs(sref).max()
+    assert np.max(np.abs(vm - vmref)) <= 1e-10 * vmref.max() and arg == argref and abs(mx - mxref) <= 1e-10 * mxref
+    assert np.array_equal(ctx.solution(), v) and np.array_equal(ctx.values(), vals0)            # ctx state untouched
+    again = ctx.stresses(False, True)
+    assert np.array_equal(again[1], own[1]) and again[2:] == own[2:]
+    # u = None → the stored field; same numbers as toe_stresses when the material is the ctx's
+    _, vm_n, mx_n, arg_n = ctx.calculate_stresses(None, lame=(lam0, mu0), want_vm=True)
+    assert np.array_equal(vm_n, own[1]) and (mx_n, arg_n) == own[2:]
+    with pytest.raises(pkg.TopOptError):
+        ctx.calculate_stresses(np.zeros(ctx.ndofs + 3), lame=(lam0, mu0))
+
+    # the API mirror: 3-tuple like the reference, lazy stress field indexed by 1-based cell id
+    grid = pkg.Grid(pts, cells, 10)
+    dh, cv, K, f = pkg.setup_problem(grid)
+    sf, mx_a, cell_a = pkg.calculate_stresses(g["u"], dh, cv, lam1, mu1)
+    assert cell_a == argref and abs(mx_a - mxref) <= 1e-10 * mxref and len(sf) == cells.shape[0]
+    assert np.max(np.abs(sf[argref] - s6_of(sref)[argref - 1])) <= 1e-10 * np.abs(sref).max()
+
+    # Hex8 + SIMP: parametrised model, and the same model hidden in an opaque callable (host-evaluated per cell)
+    g = golden_c2
+    pts, cells = g["points"], g["cells"].astype(np.int64)
+    grid = pkg.Grid(pts, cells, 12)
+    dh, cv, K, f = pkg.setup_problem(grid)
+    prob = fo.setup_problem(pts, cells)
+    mm = pkg.create_simp_material_model(1.0, 0.3, 1e-8, 3.0)
+    lam_e, mu_e = fo.create_simp_material_model(1.0, 0.3, 1e-8, 3.0)(g["density"])
+    sref, vmref, mxref, argref = fo.calculate_stresses(prob, g["u"], lam_e, mu_e)
+    for model in (mm, lambda rho: mm(rho)):
+        sf, mx_s, cell_s = pkg.calculate_stresses_simp(g["u"], dh, cv, model, g["density"])
+        assert cell_s == argref == int(g["max_stress_cell"]) and abs(mx_s - mxref) <= 1e-10 * mxref
+        assert np.max(np.abs(sf.von_mises - vmref)) <= 1e-10 * vmref.max()
+        assert np.max(np.abs(sf.sigma - s6_of(sref))) <= 1e-10 * np.abs(sref).max()
+    with pytest.raises(pkg.TopOptError):
+        pkg.calculate_stresses_simp(g["u"], dh, cv, mm, g["density"][:-1])
+    dh.ctx.close()
+
+
 # ----------------------------------------------------------------------------------------------------------
 # the reference's own test recipes through the API mirror
 # ----------------------------------------------------------------------------------------------------------

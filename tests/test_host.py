@@ -69,3 +69,55 @@ def test_solver_config(pkg):
         pkg.SolverConfig(method="gmres")
     with pytest.raises(pkg.TopOptError):
         pkg.SolverConfig(preconditioner="ilu")
+
+
+def test_get_face_nodes(pkg):
+    """Ferrite's local face tables as the reference restates them (FiniteElementAnalysis.jl:42-58)."""
+    assert pkg.get_face_nodes(4) == [(1, 3, 2), (1, 2, 4), (2, 3, 4), (1, 4, 3)]
+    hexf = pkg.get_face_nodes(np.arange(1, 9))
+    assert hexf == [(1, 4, 3, 2), (1, 2, 6, 5), (2, 3, 7, 6), (3, 4, 8, 7), (1, 5, 8, 4), (5, 6, 7, 8)]
+    pts, cells = pkg.meshgen.cantilever(2, 1, 1)
+    assert pkg.get_face_nodes(pkg.Grid(pts, cells, 10)) == pkg.get_face_nodes(4)
+    # every face is outward-oriented on the reference cell (the property FacetValues integration relies on)
+    ref = {4: np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], float),
+           8: np.array([(-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1)], float)}
+    for npc, X in ref.items():
+        c = X.mean(axis=0)
+        for face in pkg.get_face_nodes(npc):
+            P = X[np.array(face) - 1]
+            n = np.cross(P[1] - P[0], P[2] - P[0])
+            assert n @ (P.mean(axis=0) - c) > 0
+    with pytest.raises(pkg.TopOptError):
+        pkg.get_face_nodes(3)
+
+
+@pytest.mark.parametrize("hexm", [False, True])
+def test_export_boundary_conditions(pkg, tmp_path, hexm):
+    """ResultsExport.jl:108-193 restated literally (loop over cells, faces in `get_faces` order) against the vectorised writer."""
+    pts, cells = pkg.meshgen.cantilever(4, 2, 2, hex=hexm)
+    grid = pkg.Grid(pts, cells, 12 if hexm else 10)
+    fixed = set(pkg.meshgen.nodes_at_plane(pts, 0, 0.0).tolist())
+    force = set(pkg.meshgen.nodes_at_plane(pts, 0, 60.0).tolist()) | {sorted(fixed)[0]}      # one node carries both marks: force wins (:124-130)
+    out = pkg.export_boundary_conditions(grid, None, fixed, force, str(tmp_path / "bc"))
+    m = pkg.vtu.read_vtu(out, cell_types=(5, 9))
+    bc = np.zeros(pts.shape[0] + 1, dtype=int)
+    for n in fixed:
+        bc[n] = 1
+    for n in force:
+        bc[n] = 2
+    faces_of = ([(0, 1, 2), (0, 1, 3), (1, 2, 3), (0, 2, 3)] if not hexm else
+                [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7)])
+    exp_faces, exp_types = [], []
+    for cell in cells:
+        for fc in faces_of:
+            nodes = [int(cell[i]) for i in fc]
+            t = {int(bc[n]) for n in nodes}
+            if len(t) == 1 and 0 not in t:
+                exp_faces.append(nodes); exp_types.append(t.pop())
+    assert len(exp_faces) > 0 and 1 in exp_types and 2 in exp_types
+    assert m.cell_type == (9 if hexm else 5) and np.array_equal(m.cells, np.array(exp_faces))
+    assert m.cell_data["boundary_type"].dtype.kind == "i" and np.array_equal(m.cell_data["boundary_type"], exp_types)
+    assert np.array_equal(m.points, pts)
+    # no marked face at all: an empty (but valid) file, like the reference
+    out2 = pkg.export_boundary_conditions(grid, None, set(), set(), str(tmp_path / "bc_empty"))
+    assert os.path.getsize(out2) > 0

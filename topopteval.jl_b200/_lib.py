@@ -84,6 +84,9 @@ SIGNATURES = {
     "toe_energy": (C.c_int, [_P, _D, _D, _D]),
     "toe_energy_assembled": (C.c_int, [_P, _D]),
     "toe_stresses": (C.c_int, [_P, _D, _D, _D, _I64]),
+    "toe_calculate_stresses": (C.c_int, [_P, _D, C.c_double, C.c_double, _D, _D, _D, _I64]),
+    "toe_calculate_stresses_simp": (C.c_int, [_P, _D, C.c_double, C.c_double, C.c_double, C.c_double, _D, _D, _D, _D, _I64]),
+    "toe_calculate_stresses_lame_per_cell": (C.c_int, [_P, _D, _D, _D, _D, _D, _D, _I64]),
     "toe_spmv": (C.c_int, [_P, _D, _D, C.c_int]),
     "toe_time_spmv": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "toe_comm_unique_id": (C.c_int, [C.c_char_p]),
@@ -369,6 +372,33 @@ class Context:
         vm = np.empty(self.ne) if want_vm else None
         mx = C.c_double(); arg = C.c_int64()
         self._ck(self.lib.toe_stresses(self.h, _dp(sig), _dp(vm), C.byref(mx), C.byref(arg)))
+        return sig, vm, mx.value, arg.value
+
+    def calculate_stresses(self, u=None, lame=None, simp=None, lame_per_cell=None, want_sigma=False, want_vm=False):
+        """calculate_stresses(u, …) / calculate_stresses_simp(u, …) for ANY u (None = the stored solution) and material; exactly one
+        of lame=(λ, μ), simp=(E0, ν, Emin, p, density), lame_per_cell=(λₑ, μₑ).  Leaves K, constraints, material, solution alone."""
+        nq = 4 if self.npc == 4 else 8
+        sig = np.empty((self.ne, nq, 6)) if want_sigma else None
+        vm = np.empty(self.ne) if want_vm else None
+        mx = C.c_double(); arg = C.c_int64()
+        u = None if u is None else f64(u)
+        if u is not None and u.shape != (self.ndofs,):
+            raise TopOptError("calculate_stresses: u has %d entries, the problem has %d DOFs" % (u.size, self.ndofs))
+        out = (_dp(sig), _dp(vm), C.byref(mx), C.byref(arg))
+        if lame is not None:
+            self._ck(self.lib.toe_calculate_stresses(self.h, _dp(u), float(lame[0]), float(lame[1]), *out))
+        elif simp is not None:
+            rho = f64(simp[4])
+            if rho.shape != (self.ne,):
+                raise TopOptError("calculate_stresses_simp: density_data has %d entries, the mesh has %d cells" % (rho.size, self.ne))
+            self._ck(self.lib.toe_calculate_stresses_simp(self.h, _dp(u), float(simp[0]), float(simp[1]), float(simp[2]), float(simp[3]), _dp(rho), *out))
+        elif lame_per_cell is not None:
+            le, me = f64(lame_per_cell[0]), f64(lame_per_cell[1])
+            if le.shape != (self.ne,) or me.shape != (self.ne,):
+                raise TopOptError("calculate_stresses: per-cell material arrays must have one entry per cell")
+            self._ck(self.lib.toe_calculate_stresses_lame_per_cell(self.h, _dp(u), _dp(le), _dp(me), *out))
+        else:
+            raise TopOptError("calculate_stresses: no material given")
         return sig, vm, mx.value, arg.value
 
     def spmv(self, x, matrix_free=False):

@@ -26,7 +26,8 @@ __all__ = [
     "apply_fixed_boundary", "apply_sliding_boundary", "apply_force",
     "apply_volume_force", "apply_gravity", "apply_acceleration", "apply_variable_density_volume_force",
     "solve_system", "solve_system_simp", "solve_system_robust", "solve_system_robust_simp", "solve_system_adaptive",
-    "SolverConfig", "export_results", "TopOptError",
+    "calculate_stresses", "calculate_stresses_simp", "get_face_nodes",
+    "SolverConfig", "export_results", "export_boundary_conditions", "TopOptError",
     "select_nodes_by_plane", "select_nodes_by_circle", "get_node_dofs",
     "get_boundary_facets", "compute_boundary_area", "apply_surface_traction", "apply_uniform_surface_traction",
 ]
@@ -383,16 +384,17 @@ class SolverConfig:
 
 class StressField:
     """Lazy stand-in for the reference's Dict{Int,Vector{SymmetricTensor}}: `sf[cell_id]` → (nqp,6) array
-    (xx,yy,zz,xy,yz,xz); nothing is copied from the device until it is asked for."""
+    (xx,yy,zz,xy,yz,xz); nothing is copied from the device until it is asked for (`fetch` = the call that produces it)."""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, fetch=None):
         self.ctx = ctx
+        self._fetch_fn = fetch or (lambda: ctx.stresses(True, True))
         self._sigma = None
         self._vm = None
 
     def _fetch(self):
         if self._sigma is None:
-            self._sigma, self._vm, _, _ = self.ctx.stresses(True, True)
+            self._sigma, self._vm, _, _ = self._fetch_fn()
 
     @property
     def sigma(self):
@@ -407,6 +409,56 @@ class StressField:
 
     def __len__(self):
         return self.ctx.ne
+
+
+def _material_kwargs(material_model, density_data, ne):
+    density_data = np.asarray(density_data, dtype=np.float64)
+    if density_data.shape != (ne,):
+        raise TopOptError("density_data has %d entries, the mesh has %d cells" % (density_data.size, ne))
+    if isinstance(material_model, SimpMaterialModel):
+        return {"simp": (material_model.E0, material_model.nu, material_model.Emin, material_model.p, density_data)}
+    lm = [material_model(float(r)) for r in density_data]        # arbitrary callable ρ ↦ (λ, μ), evaluated per cell like :744-745
+    return {"lame_per_cell": (np.array([a for a, _ in lm]), np.array([b for _, b in lm]))}
+
+
+def calculate_stresses(u, dh, cellvalues, lam, mu):
+    """`calculate_stresses(u, dh, cellvalues, λ, μ)` (FiniteElementAnalysis.jl:440-509): stresses of ANY displacement vector
+    under ANY (λ, μ) → `(stress_field, max_von_mises, max_stress_cell)`.  One per-cell kernel + arg-max on the GPU; the
+    σ arrays come to the host only when `stress_field` is indexed."""
+    ctx = dh.ctx
+    u = np.array(u, dtype=np.float64)                           # the field belongs to this call, not to the ctx's solution
+    _, _, max_vm, max_cell = ctx.calculate_stresses(u, lame=(lam, mu))
+    return StressField(ctx, lambda: ctx.calculate_stresses(u, lame=(lam, mu), want_sigma=True, want_vm=True)), max_vm, max_cell
+
+
+def calculate_stresses_simp(u, dh, cellvalues, material_model, density_data):
+    """`calculate_stresses_simp(u, dh, cellvalues, material_model, density_data)` (FiniteElementAnalysis.jl:730-801)."""
+    ctx = dh.ctx
+    u = np.array(u, dtype=np.float64)
+    kw = _material_kwargs(material_model, density_data, ctx.ne)
+    _, _, max_vm, max_cell = ctx.calculate_stresses(u, **kw)
+    return StressField(ctx, lambda: ctx.calculate_stresses(u, want_sigma=True, want_vm=True, **kw)), max_vm, max_cell
+
+
+#: Ferrite's local face → local node tables (FiniteElementAnalysis.jl:42-58), 1-based like the reference
+_FACE_NODES = {
+    4: [(1, 3, 2), (1, 2, 4), (2, 3, 4), (1, 4, 3)],
+    8: [(1, 4, 3, 2), (1, 2, 6, 5), (2, 3, 7, 6), (3, 4, 8, 7), (1, 5, 8, 4), (5, 6, 7, 8)],
+}
+
+
+def get_face_nodes(cell):
+    """`get_face_nodes(cell)` (FiniteElementAnalysis.jl:42-58): `cell` is a connectivity row (4 or 8 node ids), a Grid, or the
+    number of nodes per cell."""
+    if isinstance(cell, Grid):
+        npc = cell.cells.shape[1]
+    elif np.isscalar(cell):
+        npc = int(cell)
+    else:
+        npc = len(cell)
+    if npc not in _FACE_NODES:
+        raise TopOptError("get_face_nodes: only Tetrahedron (4 nodes) and Hexahedron (8 nodes) cells are supported, got %d nodes" % npc)
+    return list(_FACE_NODES[npc])
 
 
 #: direct-solve entry points run PCG to this tolerance (no factorisation on the GPU path; the reference's
@@ -481,6 +533,31 @@ def export_results(data, dh, output_file: str):
     idx = nfd[ok] - 1
     un[ok] = np.stack([u[idx], u[idx + 1], u[idx + 2]], axis=1)
     return vtu.write_vtu(output_file, grid.nodes, grid.cells, grid.cell_type, point_data={"u": un})
+
+
+#: face tables of `get_faces` in ResultsExport.jl:197-217 (NOT Ferrite's order — the export has its own)
+_EXPORT_FACES = {
+    4: [(0, 1, 2), (0, 1, 3), (1, 2, 3), (0, 2, 3)],
+    8: [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7)],
+}
+
+
+def export_boundary_conditions(grid: Grid, dh, fixed_nodes, force_nodes, output_file: str):
+    """`export_boundary_conditions(grid, dh, fixed_nodes, force_nodes, file)` (ResultsExport.jl:108-193): every cell face whose
+    nodes all carry the same mark (1 = fixed, 2 = force; force overrides fixed, :124-130) becomes a VTK_TRIANGLE / VTK_QUAD with
+    cell data `boundary_type`, in cell order then face order (interior faces shared by two cells appear twice, as in the reference)."""
+    print("Exporting mesh with boundary conditions to %s..." % output_file)
+    nn = grid.nodes.shape[0]
+    bc = np.zeros(nn + 1, dtype=np.int64)
+    bc[np.asarray(sorted(fixed_nodes), dtype=np.int64)] = 1
+    bc[np.asarray(sorted(force_nodes), dtype=np.int64)] = 2
+    faces = np.asarray(_EXPORT_FACES[grid.cells.shape[1]])
+    fn = grid.cells[:, faces]                                    # (ne, nfaces, nodes per face), 1-based node ids
+    t = bc[fn]
+    keep = np.all(t == t[..., :1], axis=2) & (t[..., 0] != 0)
+    out = vtu.write_vtu(output_file, grid.nodes, fn[keep], 5 if faces.shape[1] == 3 else 9, cell_data={"boundary_type": t[..., 0][keep]})
+    print("Boundary conditions successfully exported to %s" % out)
+    return out
 
 
 def calculate_volume(grid: Grid, density_data=None) -> float:

@@ -19,6 +19,7 @@ int time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, doub
 int energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem_host);
 int energy_assembled(toe_ctx* ctx, double* half_uKu);
 int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell);
+int stresses_with(toe_ctx* ctx, const Material& mat, const double* u_dev, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell);
 int dist_comm_unique_id(char id_out[128], std::string& err);
 int dist_comm_init(toe_ctx* ctx, int nranks, int rank, const char id[128]);
 int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, const int64_t* conn);
@@ -287,6 +288,49 @@ int toe_energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_e
 int toe_energy_assembled(toe_ctx* ctx, double* half_uKu) { GUARD(ctx); return energy_assembled(ctx, half_uKu); }
 int toe_stresses(toe_ctx* ctx, double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell) {
     GUARD(ctx); return stresses(ctx, sigma, von_mises, max_von_mises, max_stress_cell);
+}
+
+// calculate_stresses(u, dh, cv, λ, μ) / calculate_stresses_simp(u, dh, cv, material_model, density_data): any u, any material,
+// nothing of the ctx's own state is changed (u goes to the scratch vector, per-cell material data to temporaries)
+static int stresses_for(toe_ctx* ctx, const double* u, Material mat, const double* a_host, const double* b_host,
+                        double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell) {
+    if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "calculate_stresses: DOFs not built (setup_problem)");
+    TRY(ensure_vectors(ctx));
+    const double* u_dev = ctx->u.p;
+    if (u) { TRY(set_vec(ctx, u, ctx->tmp.p)); u_dev = ctx->tmp.p; }
+    else if (!ctx->have_solution) return toe_fail(ctx, TOE_ERR_STATE, "calculate_stresses: no displacement vector given and none stored");
+    DevBuf<double> a, b;
+    const double* hosts[2] = {a_host, b_host};
+    DevBuf<double>* devs[2] = {&a, &b};
+    for (int k = 0; k < 2; k++) {
+        if (!hosts[k]) continue;
+        CU(devs[k]->alloc(ctx->ne));
+        if (dist_active(ctx)) TRY(dist_localize_cells(ctx, hosts[k], devs[k]->p));          // per-cell data is indexed by global cell id
+        else CU(cudaMemcpyAsync(devs[k]->p, hosts[k], ctx->ne * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (mat.mode == MAT_SIMP) mat.density = a.p;
+    if (mat.mode == MAT_PERCELL) { mat.lam_e = a.p; mat.mu_e = b.p; }
+    return stresses_with(ctx, mat, u_dev, sigma, von_mises, max_von_mises, max_stress_cell);     // synchronises before the temporaries go
+}
+int toe_calculate_stresses(toe_ctx* ctx, const double* u, double lambda, double mu,
+                           double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell) {
+    GUARD(ctx);
+    Material m = Material(); m.mode = MAT_UNIFORM; m.lambda = lambda; m.mu = mu;
+    return stresses_for(ctx, u, m, nullptr, nullptr, sigma, von_mises, max_von_mises, max_stress_cell);
+}
+int toe_calculate_stresses_simp(toe_ctx* ctx, const double* u, double E0, double nu, double Emin, double p, const double* density,
+                                double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell) {
+    GUARD(ctx);
+    if (!density) return toe_fail(ctx, TOE_ERR_ARG, "calculate_stresses_simp: density_data is required");
+    Material m = Material(); m.mode = MAT_SIMP; m.E0 = E0; m.nu = nu; m.Emin = Emin; m.p = p;
+    return stresses_for(ctx, u, m, density, nullptr, sigma, von_mises, max_von_mises, max_stress_cell);
+}
+int toe_calculate_stresses_lame_per_cell(toe_ctx* ctx, const double* u, const double* lambda_e, const double* mu_e,
+                                         double* sigma, double* von_mises, double* max_von_mises, int64_t* max_stress_cell) {
+    GUARD(ctx);
+    if (!lambda_e || !mu_e) return toe_fail(ctx, TOE_ERR_ARG, "calculate_stresses: per-cell material needs lambda and mu vectors");
+    Material m = Material(); m.mode = MAT_PERCELL;
+    return stresses_for(ctx, u, m, lambda_e, mu_e, sigma, von_mises, max_von_mises, max_stress_cell);
 }
 
 int toe_surface_nodes(toe_ctx* ctx, int64_t* nodes_out, int64_t* count_out) { GUARD(ctx); return select_nodes(ctx, 0, nullptr, nullptr, 0.0, 0.0, nodes_out, count_out); }

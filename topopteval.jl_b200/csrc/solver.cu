@@ -902,9 +902,18 @@ __global__ void k_argmax_final(const double* __restrict__ bmax, const int* __res
 int dist_sum_per_element_w(toe_ctx* ctx, const double* local_dev, double* global_host, int width);
 int dist_argmax(toe_ctx* ctx, double* max_inout, i64* cell_inout);
 
+int stresses_with(toe_ctx* ctx, const Material& mat, const double* u_dev, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell);
+
 int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell) {
     if (!ctx->have_dofs || ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "stresses: mesh/material not set");
     TRY(ensure_vectors(ctx));
+    return stresses_with(ctx, ctx->mat, ctx->u.p, sigma_host, vm_host, max_vm, max_cell);
+}
+
+// stress recovery for ANY displacement vector and material (calculate_stresses(u, dh, cv, λ, μ) is a free function in the reference:
+// FiniteElementAnalysis.jl:440 / :730); reads the mesh only — K, constraints, material and solution of the ctx stay as they are
+int stresses_with(toe_ctx* ctx, const Material& mat, const double* u_dev, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell) {
+    if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "stresses: DOFs not built");
     int ne = (int)ctx->ne;
     int nqp = ctx->npc == 4 ? 4 : 8;
     unsigned grid = div_up(ne, 128);
@@ -913,8 +922,8 @@ int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, 
     if (vm_host) CU(vm.alloc(ne));
     CU(bmax.alloc(grid + 1)); CU(barg.alloc(grid + 1));
     double* sp = sigma_host ? sig.p : nullptr; double* vp = vm_host ? vm.p : nullptr;
-    if (ctx->npc == 4) LAUNCH(ctx, k_stress<4>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, (const double*)ctx->u.p, sp, vp, ne, bmax.p, barg.p);
-    else               LAUNCH(ctx, k_stress<8>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, (const double*)ctx->u.p, sp, vp, ne, bmax.p, barg.p);
+    if (ctx->npc == 4) LAUNCH(ctx, k_stress<4>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, mat, u_dev, sp, vp, ne, bmax.p, barg.p);
+    else               LAUNCH(ctx, k_stress<8>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, mat, u_dev, sp, vp, ne, bmax.p, barg.p);
     LAUNCH(ctx, k_argmax_final, 1, 1024, 0, (const double*)bmax.p, (const int*)barg.p, (int)grid, bmax.p + grid, barg.p + grid);
     double hm = 0; int ha = 0;
     CU(cudaMemcpyAsync(&hm, bmax.p + grid, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

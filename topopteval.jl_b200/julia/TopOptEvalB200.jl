@@ -25,6 +25,7 @@ export setup_problem, create_material_model, create_simp_material_model,
        apply_fixed_boundary!, apply_sliding_boundary!, apply_force!,
        apply_volume_force!, apply_gravity!, apply_acceleration!, apply_variable_density_volume_force!,
        solve_system, solve_system_simp, solve_system_robust, solve_system_robust_simp, solve_system_adaptive,
+       calculate_stresses, calculate_stresses_simp,
        SolverConfig, element_energies, compliance,
        select_nodes_by_plane, select_nodes_by_circle, get_node_dofs, get_boundary_facets, compute_boundary_area,
        apply_surface_traction!, apply_uniform_surface_traction!
@@ -191,15 +192,59 @@ struct PcgStats
     coarse_dofs::Int64; precond_seconds::Float64
 end
 
-"Lazy stand-in for Dict{Int,Vector{SymmetricTensor}}: nothing leaves the GPU until indexed."
-mutable struct StressField; ctx::Ctx; ne::Int; nqp::Int; sigma::Union{Nothing,Array{Float64,3}}; end
+"Lazy stand-in for Dict{Int,Vector{SymmetricTensor}}: nothing leaves the GPU until indexed (`fetch!` fills a 6 × nqp × ne array)."
+mutable struct StressField; ctx::Ctx; ne::Int; nqp::Int; sigma::Union{Nothing,Array{Float64,3}}; fetch!::Function; end
+_fetch_stored(c::Ctx) = sig -> begin
+    mx = Ref(0.0); arg = Ref{Int64}(0)
+    check(c, ccall((:toe_stresses, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}), c.ptr, sig, C_NULL, mx, arg))
+end
+StressField(c::Ctx, ne::Int, nqp::Int, sigma) = StressField(c, ne, nqp, sigma, _fetch_stored(c))
 function Base.getindex(s::StressField, cell::Int)
     if s.sigma === nothing
-        sig = Array{Float64,3}(undef, 6, s.nqp, s.ne); mx = Ref(0.0); arg = Ref{Int64}(0)
-        check(s.ctx, ccall((:toe_stresses, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}), s.ctx.ptr, sig, C_NULL, mx, arg))
+        sig = Array{Float64,3}(undef, 6, s.nqp, s.ne)
+        s.fetch!(sig)
         s.sigma = sig
     end
     return [SymmetricTensor{2,3}((v[1], v[4], v[6], v[2], v[5], v[3])) for v in eachcol(@view s.sigma[:, :, cell])]
+end
+Base.length(s::StressField) = s.ne
+Base.haskey(s::StressField, cell::Int) = 1 <= cell <= s.ne
+Base.keys(s::StressField) = 1:s.ne
+
+# ---- calculate_stresses(u, dh, cv, λ, μ) (:440-509) and calculate_stresses_simp(u, dh, cv, material_model, density_data) (:730-801) ----
+# free functions in the reference: ANY displacement vector, ANY material; the ctx's K, constraints, material and solution stay untouched
+function _stress_call(dh::B200DofHandler, u::Vector{Float64}, kind::Symbol, a, b)
+    c = dh.ctx
+    length(u) == dh.ndofs || error("calculate_stresses: u has $(length(u)) entries, the problem has $(dh.ndofs) DOFs")
+    run = sig -> begin
+        mx = Ref(0.0); arg = Ref{Int64}(0)
+        sp = sig === nothing ? Ptr{Float64}(C_NULL) : pointer(sig)
+        GC.@preserve sig u a b begin
+            if kind === :lame
+                check(c, ccall((:toe_calculate_stresses, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}),
+                               c.ptr, u, a, b, sp, C_NULL, mx, arg))
+            elseif kind === :simp
+                check(c, ccall((:toe_calculate_stresses_simp, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}),
+                               c.ptr, u, a.E0, a.nu, a.Emin, a.p, b, sp, C_NULL, mx, arg))
+            else
+                check(c, ccall((:toe_calculate_stresses_lame_per_cell, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}),
+                               c.ptr, u, a, b, sp, C_NULL, mx, arg))
+            end
+        end
+        return mx[], Int(arg[])
+    end
+    max_vm, max_cell = run(nothing)
+    ne = getncells(dh.grid); nqp = length(dh.grid.cells[1].nodes) == 4 ? 4 : 8
+    return StressField(c, ne, nqp, nothing, sig -> run(sig)), max_vm, max_cell
+end
+calculate_stresses(u, dh::B200DofHandler, cellvalues, λ, μ) = _stress_call(dh, convert(Vector{Float64}, copy(u)), :lame, Float64(λ), Float64(μ))
+function calculate_stresses_simp(u, dh::B200DofHandler, cellvalues, material_model, density_data)
+    ρ = convert(Vector{Float64}, density_data)
+    length(ρ) == getncells(dh.grid) || error("density_data has $(length(ρ)) entries, the grid has $(getncells(dh.grid)) cells")
+    uu = convert(Vector{Float64}, copy(u))
+    material_model isa SimpModel && return _stress_call(dh, uu, :simp, material_model, ρ)
+    lm = material_model.(ρ)                                  # arbitrary closure: evaluated on the host, per cell (:744-745)
+    return _stress_call(dh, uu, :percell, first.(lm), last.(lm))
 end
 
 const DIRECT_EQUIVALENT_TOL = 1e-10      # `K \ f` entry points run PCG to the accuracy the reference's direct solve reaches

@@ -61,7 +61,12 @@ def _read_appended(blob: bytes, offset: int, dtype: str, compressed: bool, hdr: 
     return np.frombuffer(blob[p:p + nbytes], dtype=dtype)
 
 
-def read_vtu(path: str) -> VtuMesh:
+_NODES_PER_CELL = {5: 3, 9: 4, VTK_TETRA: 4, VTK_HEXAHEDRON: 8}
+
+
+def read_vtu(path: str, cell_types=(VTK_TETRA, VTK_HEXAHEDRON)) -> VtuMesh:
+    """`cell_types`: VTK types accepted as the dominant type — volume meshes by default (`import_mesh`); pass (5, 9) to read back
+    the triangle / quad file `export_boundary_conditions` writes."""
     raw = open(path, "rb").read()
     m = re.search(rb"<AppendedData[^>]*>\s*_", raw)
     xml = raw[: m.start()] if m else raw
@@ -99,9 +104,9 @@ def read_vtu(path: str) -> VtuMesh:
     # dominant-type selection, as MeshImport.jl:97-125 does
     vals, counts = np.unique(types, return_counts=True)
     dom = int(vals[np.argmax(counts)])
-    if dom not in (VTK_TETRA, VTK_HEXAHEDRON):
+    if dom not in cell_types or dom not in _NODES_PER_CELL:
         raise ValueError("only Tet4 (10) / Hex8 (12) meshes are on the hot path, got VTK type %d" % dom)
-    npc = 4 if dom == VTK_TETRA else 8
+    npc = _NODES_PER_CELL[dom]
     starts = np.concatenate(([0], offs[:-1]))
     sel = np.nonzero(types == dom)[0]
     idx = starts[sel][:, None] + np.arange(npc)[None, :]
@@ -148,8 +153,12 @@ def write_vtu(path: str, points: np.ndarray, cells_1based: np.ndarray, cell_type
     add("Cells", "types", np.full(ne, cell_type, dtype="u1"), "UInt8", 1)
     for sec, dd in (("PointData", point_data or {}), ("CellData", cell_data or {})):
         for k, v in dd.items():
-            v = np.ascontiguousarray(v, dtype="<f8")
-            add(sec, k, v, "Float64", 1 if v.ndim == 1 else v.shape[1])
+            v = np.asarray(v)
+            if np.issubdtype(v.dtype, np.integer):         # WriteVTK keeps Int data as Int64 (boundary_type, ResultsExport.jl:189)
+                v = np.ascontiguousarray(v, dtype="<i8"); vt = "Int64"
+            else:
+                v = np.ascontiguousarray(v, dtype="<f8"); vt = "Float64"
+            add(sec, k, v, vt, 1 if v.ndim == 1 else v.shape[1])
     lines = ['<?xml version="1.0" encoding="utf-8"?>',
              '<VTKFile type="UnstructuredGrid" version="1.0" byte_order="LittleEndian" header_type="UInt64" '
              'compressor="vtkZLibDataCompressor">', "  <UnstructuredGrid>",
