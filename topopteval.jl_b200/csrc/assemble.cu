@@ -682,6 +682,7 @@ int compute_diag(toe_ctx* ctx) {
             LAUNCH(ctx, k_diag_ebe<8>, div_up(ctx->nq, 128), 128, 0, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->cq.p,
                    (const double*)ctx->xq.p, ctx->mat, ctx->diag.p, ctx->nq);
     }
+    TRY(dist_align(ctx));                        // first exchange of a step: the ranks enter it together
     TRY(dist_post_spmv(ctx, ctx->diag.p));      // sub-assembled partitions: sum the interface contributions
     if (ctx->any_dirichlet)
         LAUNCH(ctx, k_diag_override, div_up((i64)n, 256), 256, 0, (const unsigned char*)ctx->dflag.p, (const double*)ctx->dval.p, ctx->diag.p, n);

@@ -296,6 +296,8 @@ int op_apply(toe_ctx* ctx, const double* x, double* y, int matrix_free, double* 
 double op_bytes(toe_ctx* ctx, int matrix_free);
 int dist_post_spmv(toe_ctx* ctx, double* y);      // interface sum (no-op without dist)
 int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count);
+int dist_align(toe_ctx* ctx);                     // ranks' streams meet (no-op without dist); see dist.cu
+static const int PARTIALS_ALIGN_SLOT = 3 * (N_SM * 8) + 16;   // scratch double of dist_align inside ctx->partials (after the k_norms outputs)
 int mesh_build_tiles(toe_ctx* ctx);
 int ebe_tile_launch(toe_ctx* ctx, const double* x, double* y, CGScalars* cg, bool mask, const int* done_flag, double* dot_out);
 int dist_sum_per_element(toe_ctx* ctx, const double* local_dev, double* global_host);   // per-cell output, global cell order

@@ -149,6 +149,21 @@ int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count) {
     return TOE_OK;
 }
 
+// Rendezvous of the ranks' streams: one 8-byte allreduce, then the host waits for it.  Set-up work differs per rank (host-side map
+// building, partition sizes), so the ranks reach the first exchange of a step up to ~100 ms apart; every broken-down partitioned solve
+// seen in round 1 was the FIRST solve after a set-up, the only place where such a skew exists.  Entering the exchange
+// sequences of a step in lock-step costs two ~20 µs collectives per step.
+int dist_align(toe_ctx* ctx) {
+    DistState* d = ctx->dist;
+    if (!d || d->nranks == 1) return TOE_OK;
+    TRY(ensure_vectors(ctx));
+    double* slot = ctx->partials.p + PARTIALS_ALIGN_SLOT;
+    CU(cudaMemsetAsync(slot, 0, sizeof(double), ctx->stream));
+    NC(g_nccl.AllReduce(slot, slot, 1, ncclDouble, ncclSum, d->comm, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TOE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // recursive coordinate bisection by exact radix selection on (quantised centroid coordinate, cell id) keys
 // ---------------------------------------------------------------------------------------------------------
@@ -403,7 +418,7 @@ int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, cons
     CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
     TRY(mailbox_setup(ctx, d, if_src));
     TRY(dist_warm_up(ctx));
-    return TOE_OK;
+    return dist_align(ctx);
 }
 
 // ---------------------------------------------------------------------------------------------------------

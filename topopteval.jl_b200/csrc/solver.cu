@@ -566,6 +566,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     int CG_BATCH = CG_BATCH_DEFAULT;
     if (const char* eb = getenv("TOE_CG_BATCH")) { int v = atoi(eb); if (v >= 2) CG_BATCH = v & ~1; }
 
+    if (dist) TRY(dist_align(ctx));            // the ranks start the iteration's exchange sequence in lock-step (outside the timed solve)
     EventPair ev; CU(ev.create());
     cudaEvent_t e0 = ev.a, e1 = ev.b;
     CU(cudaEventRecord(e0, ctx->stream));
