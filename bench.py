@@ -310,8 +310,11 @@ def run_b200(args, pkg):
     # extra, not part of `value`: the same solve with the two-level preconditioner, run in a CHILD process so
     # that nothing it does can touch the measurements above (this ctx stays alive; the GPU has room for both)
     two_level = None
+    variants = None
     if world == 1 and not args.no_two_level and rank == 0:
         two_level = two_level_probe_in_child(args, e, stage_acc["solve"] / args.steps)
+    if world == 1 and not getattr(args, "no_variants", False) and not mf and rank == 0:
+        variants = variant_probes_in_children(args)
 
     h2d = pts.nbytes + cells.nbytes + load.nbytes + pres.nbytes
     d2h = u.nbytes + 2 * 8 + 128
@@ -342,7 +345,7 @@ def run_b200(args, pkg):
                        "spmv_gbs": spmv_bytes / spmv_s / 1e9, "energy_ms": 1e3 * stage_acc["energy"] / args.steps,
                        "energy": e, "compliance": c, "local_sizes": sizes,
                        "setup_ms": {k: 1e3 * tm_setup[k] for k in ("set_mesh", "build_dofs", "build_pattern")},
-                       "two_level_preconditioner": two_level},
+                       "two_level_preconditioner": two_level, "variants": variants},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_step(pkg, CPU_SAMPLE)
@@ -395,6 +398,29 @@ def two_level_probe_in_child(args, energy_jacobi, jacobi_pcg_seconds):
         return {"error": str(ex)[:300]}
 
 
+def variant_probes_in_children(args):
+    """N=1 extra, not part of `value`: the opt-in kernel variants (ROWS assembly, pipelined matrix-free operator) timed next to their
+    defaults on the same workload by tools/variants_probe.py — one CHILD process per section, so that a kernel that has not met
+    real hardware yet can fault without touching the headline measurement (this process's ctx stays alive meanwhile)."""
+    size = {"C4_10M": "10M", "C3_1M": "1M", "200k": "200k", "toy": "toy"}.get(args.workload)
+    if size is None:
+        return None
+    out = {}
+    for key, section in (("assembly", "asm"), ("matrix_free_operator", "ebe")):
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "variants_probe.py"), size, "--only", section]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=150, cwd=ROOT)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode != 0 or not lines:
+                out[key] = {"error": ("rc=%d " % r.returncode) + (r.stderr or r.stdout)[-300:]}
+            else:
+                out[key] = json.loads(lines[-1]).get(key)
+        except Exception as ex:  # noqa: BLE001 — an optional extra must never cost the headline number
+            out[key] = {"error": str(ex)[:300]}
+    out["note"] = "opt-in variants next to their defaults, separate processes; reported for comparison, never in `value`"
+    return out
+
+
 def profile_traffic(matrix_free):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/*.json), else None."""
     p = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
@@ -414,6 +440,7 @@ def main():
     ap.add_argument("--matrix-free", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-two-level", action="store_true", help="skip the extra two-level-preconditioner solve reported in stages")
+    ap.add_argument("--no-variants", action="store_true", help="skip the opt-in kernel variants (child processes) reported in stages.variants")
     args = ap.parse_args()
     import __graft_entry__ as graft
     pkg = graft.load_package()

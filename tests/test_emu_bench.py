@@ -22,7 +22,7 @@ def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
-    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=mf, no_cpu_baseline=True, no_two_level=mf)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=mf, no_cpu_baseline=True, no_two_level=mf, no_variants=False)
     def probe_in_process(a, energy_jacobi, jacobi_s):             # the child process of the real bench, in-process on the emulated build
         b2 = io.StringIO()
         with redirect_stdout(b2):
@@ -31,6 +31,7 @@ def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
         d2["energy_rel_diff_vs_jacobi"] = abs(d2["energy"] - energy_jacobi) / abs(energy_jacobi)
         return d2
     monkeypatch.setattr(bench, "two_level_probe_in_child", probe_in_process)
+    monkeypatch.setattr(bench, "variant_probes_in_children", lambda a: {"assembly": {"stub": True}, "note": "stubbed: the children need a GPU"})
     buf = io.StringIO()
     with emu_support.emulated(pkg, lib), redirect_stdout(buf):
         bench.run_b200(args, pkg)
@@ -48,5 +49,6 @@ def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     assert d["stages"]["pcg_converged"] and d["stages"]["pcg_iterations"] > 0 and d["stages"]["energy"] > 0
+    assert (d["stages"]["variants"] is None) == mf
     tl = d["stages"]["two_level_preconditioner"]
     assert (mf and tl is None) or "error" not in tl and tl["converged"] and tl["pcg_iterations"] < d["stages"]["pcg_iterations"] and tl["energy_rel_diff_vs_jacobi"] < 1e-6

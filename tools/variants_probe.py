@@ -14,11 +14,19 @@ import __graft_entry__ as graft
 
 pkg = graft.load_package()
 A = pkg._lib
+if os.environ.get("TOE_TEST_EMU") == "1":          # dry run of this tool's plumbing where there is no GPU (tests/cuda_emu: never a measurement)
+    sys.path.insert(0, "tests")
+    import emu_support
+    pkg._lib._lib = emu_support.load_emu()[1]
 
 
 def main():
-    which = sys.argv[1] if len(sys.argv) > 1 else "1M"
-    dims = {"small": (48, 16, 6), "200k": (96, 32, 12), "1M": (120, 50, 28), "10M": (260, 110, 58)}[which]
+    argv = [a for a in sys.argv[1:]]
+    only = None                                    # --only asm|ebe|pc: one section (bench.py runs each in its own child process)
+    if "--only" in argv:
+        i = argv.index("--only"); only = argv[i + 1]; del argv[i:i + 2]
+    which = argv[0] if argv else "1M"
+    dims = {"toy": (8, 3, 2), "small": (48, 16, 6), "200k": (96, 32, 12), "1M": (120, 50, 28), "10M": (260, 110, 58)}[which]
     pts, cells = pkg.meshgen.cantilever(*dims)
     ctx = pkg.Context(0)
     ctx.set_mesh(pts, cells); ctx.build_dofs(); ctx.build_pattern()
@@ -27,7 +35,7 @@ def main():
     # ---- assembly variants ------------------------------------------------------------------------------------------
     asm = {}
     ref_diag = None
-    for name, var in (("gather", A.ASM_GATHER), ("rows", A.ASM_ROWS)):
+    for name, var in (("gather", A.ASM_GATHER), ("rows", A.ASM_ROWS)) if only in (None, "asm") else ():
         ts = []
         for _ in range(4):
             ctx.assemble_lame(lam, mu, var)
@@ -40,7 +48,8 @@ def main():
         asm[name] = {"ms_min": min(ts[1:]), "ms_all": ts, "elements_per_s": ctx.ne / (min(ts[1:]) * 1e-3),
                      "max_rel_diff_diag_vs_gather": float(np.max(np.abs(d - ref_diag) / np.abs(ref_diag))),
                      "max_rel_diff_Kx_vs_gather": float(np.max(np.abs(y - ref_y)) / np.max(np.abs(ref_y)))}
-    out["assembly"] = asm
+    if asm:
+        out["assembly"] = asm
     # ---- matrix-free operator variants ----------------------------------------------------------------------------
     ctx.assemble_lame(lam, mu)
     load = pkg.meshgen.nodes_at_plane(pts, 0, 60.0); fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0)
@@ -51,7 +60,7 @@ def main():
     x = np.random.default_rng(1).standard_normal(ctx.ndofs); x[pres - 1] = 0.0
     ebe = {}
     y_tile = None
-    for name, env in (("tile", None), ("pipe", "1")):
+    for name, env in (("tile", None), ("pipe", "1")) if only in (None, "ebe") else ():
         if env:
             os.environ["TOE_EBE_PIPE"] = env
         else:
@@ -62,11 +71,16 @@ def main():
             y_tile = y
         ebe[name] = {"ms": s * 1e3, "GBs_algorithmic": b / s / 1e9, "bit_identical_to_tile": bool(np.array_equal(y, y_tile))}
     os.environ.pop("TOE_EBE_PIPE", None)
-    s, b = ctx.time_spmv(matrix_free=False, reps=20)
-    ebe["assembled_spmv_ms"] = s * 1e3
-    out["matrix_free_operator"] = ebe
+    if ebe:
+        s, b = ctx.time_spmv(matrix_free=False, reps=20)
+        ebe["assembled_spmv_ms"] = s * 1e3
+        out["matrix_free_operator"] = ebe
     # ---- preconditioners ----------------------------------------------------------------------------------------------
     pc = {}
+    if only not in (None, "pc"):
+        ctx.close()
+        print(json.dumps(out, default=float))
+        return
     for name, tl in (("jacobi", False), ("two_level", True)):
         t0 = time.perf_counter()
         st = ctx.solve_pcg(1e-8, 1e-8, 40000, two_level=tl)
