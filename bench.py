@@ -293,9 +293,11 @@ def run_b200(args, pkg):
     barrier()
     t0 = time.perf_counter()
     e2e_retries = 0
+    e2e_restarts = 0                                      # CG restarts inside toe_solve_pcg (partitioned runs): every e2e step is a first solve after a set-up
     for _ in range(e2e_steps):
         for attempt in range(3):                          # partitioned runs: a step whose solve broke down is repeated INSIDE the timed region
             st2, e2, c2, u = e2e_step()
+            e2e_restarts += int(st2.get("restarts", 0))
             if not any_rank(not st2["converged"]) or world == 1:
                 break
             e2e_retries += 1
@@ -332,7 +334,7 @@ def run_b200(args, pkg):
                        "wall_ms_per_step": 1e3 * wall_s / args.steps, "measurement_attempts": attempts},
             "clocks": clocks,
             "e2e": {"value": None if e2e_invalid else ne_total * e2e_steps / e2e_s, "invalid": e2e_invalid, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "repeated_steps": e2e_retries, "pcg_iterations": int(st2["niter"]), "energy": e2,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "repeated_steps": e2e_retries, "pcg_restarts": e2e_restarts, "pcg_iterations": int(st2["niter"]), "energy": e2,
                     "path": "host mesh (pinned) -> toe_set_mesh -> build_dofs -> build_pattern -> assemble -> loads -> apply! -> PCG -> energy -> u to host"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_ebe_tile+k_ebe_nodes" if mf else "k_spmv_bsr_pipe", "bound": "hbm", "achieved": spmv_bytes / spmv_s / 1e9, "peak": peaks["hbm_gbs"],
