@@ -156,6 +156,8 @@ int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count) {
 int dist_align(toe_ctx* ctx) {
     DistState* d = ctx->dist;
     if (!d || d->nranks == 1) return TOE_OK;
+    static const bool off = getenv("TOE_DIST_NO_ALIGN") != nullptr;      // A/B switch for tools/dist_resetup_check.py
+    if (off) return TOE_OK;
     TRY(ensure_vectors(ctx));
     double* slot = ctx->partials.p + PARTIALS_ALIGN_SLOT;
     CU(cudaMemsetAsync(slot, 0, sizeof(double), ctx->stream));
