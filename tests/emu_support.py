@@ -14,11 +14,21 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
-EMU_LIB = os.path.join(EMU_DIR, "_build", "libtopopt_emu.so")
+# TOE_EMU_ASAN=1: AddressSanitizer build in its own object directory; run the tests with
+#   LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 TOE_EMU_ASAN=1 python -m pytest tests/test_emu_*.py
+ASAN = os.environ.get("TOE_EMU_ASAN") == "1"
+OBJDIR = "_asan" if ASAN else "_build"
+EMU_LIB = os.path.join(EMU_DIR, OBJDIR, "libtopopt_emu.so")
 
 
 def build_emu(extra: str = "", opt: str = "-O2") -> str:
-    res = subprocess.run(["make", "-C", EMU_DIR, "-j8", "OPT=" + opt] + (["EXTRA=" + extra] if extra else []), capture_output=True, text=True)
+    if ASAN:
+        extra = (extra + " -fsanitize=address -fno-omit-frame-pointer").strip()
+        opt = "-O1"
+    cxx = ["CXX=/usr/bin/g++"] if ASAN and os.path.exists("/usr/bin/g++") else []      # the distribution's g++ ships libasan
+    env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}                    # the sanitizer runtime is for the tests, not for make / g++
+    res = subprocess.run(["make", "-C", EMU_DIR, "-j8", "OPT=" + opt, "OBJDIR=" + OBJDIR] + cxx + (["EXTRA=" + extra] if extra else []),
+                         capture_output=True, text=True, env=env)
     if res.returncode != 0:
         raise RuntimeError("building libtopopt_emu.so failed:\n" + res.stdout[-3000:] + res.stderr[-6000:])
     return EMU_LIB
