@@ -205,7 +205,8 @@ int toe_set_mesh_distributed(toe_ctx* ctx, int64_t nn, const double* xyz, int64_
 int toe_get_partition(toe_ctx* ctx, int32_t* part_of_cell);
 int toe_local_sizes(toe_ctx* ctx, int64_t* ne_local, int64_t* ndofs_local, int64_t* nnz_local, int64_t* n_interface_dofs);
 /* transport of the per-iteration interface exchange: 0 = single GPU, 1 = NCCL send/recv + allreduce,
- * 2 = fused peer-memory kernel (CUDA IPC mailboxes over NVLink/NVSwitch; chosen when every rank can map every peer) */
+ * 2 = fused peer-memory kernel (CUDA IPC mailboxes over NVLink/NVSwitch; opt-in TOE_DIST_P2P=1, needs every rank to map every peer),
+ * 3 = one ncclAllGather per exchange carrying interface values and scalars (opt-in TOE_DIST_XCHG=allgather) */
 int toe_comm_info(toe_ctx* ctx, int* nranks, int* rank, int* transport);
 
 #ifdef __cplusplus

@@ -600,6 +600,23 @@ ncclResult_t ncclAllReduce(const void* sendbuff, void* recvbuff, size_t count, n
     memcpy(recvbuff, acc.data(), bytes);
     return ncclSuccess;
 }
+ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t dt, ncclComm_t comm, cudaStream_t) {
+    World& w = *comm->w;
+    const size_t bytes = sendcount * dt_size(dt);
+    std::vector<char> all(bytes * w.n ? bytes * w.n : 1);
+    {
+        std::unique_lock<std::mutex> lk(w.m);
+        w.send[comm->rank] = sendbuff;
+        if (!world_barrier(w, lk)) return ncclSystemError;                 // every rank's pointer is published
+        std::vector<const void*> src = w.send;
+        lk.unlock();
+        for (int r = 0; r < w.n; r++) memcpy(all.data() + (size_t)r * bytes, src[r], bytes);
+        lk.lock();
+        if (!world_barrier(w, lk)) return ncclSystemError;                 // everybody has read every send buffer (in-place safe)
+    }
+    memcpy(recvbuff, all.data(), bytes * w.n);
+    return ncclSuccess;
+}
 ncclResult_t ncclGroupStart(void) { g_group_depth++; return ncclSuccess; }
 ncclResult_t ncclGroupEnd(void) {
     if (g_group_depth <= 0) return ncclInvalidUsage;

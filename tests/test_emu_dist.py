@@ -150,6 +150,28 @@ def test_peer_memory_exchange_protocol(emu, world, dims, monkeypatch):
             assert r["it"] == nccl[rk][0]["it"] and np.array_equal(r["u"], nccl[rk][0]["u"]), (rk, rep, r["it"], nccl[rk][0]["it"])
 
 
+@pytest.mark.parametrize("world,dims,simp,mf", [(2, (12, 4, 2), False, False), (4, (12, 5, 3), True, False), (4, (16, 4, 2), False, True), (8, (24, 4, 2), False, False)])
+def test_allgather_exchange_transport(emu, world, dims, simp, mf, monkeypatch):
+    """TOE_DIST_XCHG=allgather: one ncclAllGather per exchange carries every rank's packed interface values and its partial scalars.
+    Same arithmetic and summation order as the send/recv transport → bit-identical iterates, loads, diagonals and per-cell outputs;
+    re-set-ups on the same ctx reproduce."""
+    pkg, lib = emu
+    prob = _problem(pkg, dims, simp)
+    ref = _run_ranks(pkg, world, prob, mf, repeats=1, tol=1e-9)
+    monkeypatch.setenv("TOE_DIST_XCHG", "allgather")
+    ag = _run_ranks(pkg, world, prob, mf, repeats=2, tol=1e-9)
+    assert ag[0][-1]["transport"] == "nccl-allgather" and ref[0][-1]["transport"] == "nccl"
+    for rk in range(world):
+        a = ref[rk][0]
+        for rep in range(2):
+            r = ag[rk][rep]
+            assert r["conv"] == 1 and r["restarts"] == 0 and r["it"] == a["it"], (rk, rep, r["it"], a["it"])
+            for key in ("u", "f", "diag", "ee", "vm", "vm2"):
+                assert np.array_equal(r[key], a[key]), (rk, rep, key)
+            assert r["e"] == a["e"] and r["c"] == a["c"] and r["m"] == a["m"] and (r["mx"], r["arg"]) == (a["mx"], a["arg"])
+        assert np.array_equal(ag[rk][-1]["spmv"], ref[rk][-1]["spmv"])
+
+
 @pytest.mark.parametrize("world,dims,simp,mf", [(4, (16, 4, 2), True, False), (2, (10, 4, 3), False, True)])
 def test_two_level_preconditioner_on_partitions(emu, world, dims, simp, mf, monkeypatch):
     """Jacobi + rigid-body coarse space on a partitioned ctx: per-box sums over OWNED nodes + allreduce, coarse operator probed

@@ -1,0 +1,23 @@
+"""The opt-in all-gather exchange transport (TOE_DIST_XCHG=allgather) on real GPUs: same parity bars as the default send/recv
+transport (tests/test_dist.py), through tests/dist_worker.py under torchrun.  Written after the round-1 GPU budget was spent
+(bit-identical to send/recv on the emulated build), hence the late-sorting file name; skipped when fewer than 2 GPUs are visible."""
+import pytest
+
+from test_dist import _ngpus, _torchrun
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dims,extra", [("24,8,4", []), ("48,16,6", ["simp"])])
+def test_two_gpu_allgather_transport(dims, extra):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, ["tests/dist_worker.py", dims] + extra, 29541, env={"TOE_DIST_XCHG": "allgather", "TOE_EXPECT_TRANSPORT": "nccl-allgather"})
+    assert r.returncode == 0 and "DIST PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_four_gpu_allgather_transport():
+    if _ngpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    r = _torchrun(4, ["tests/dist_worker.py", "48,16,6"], 29542, timeout=400, env={"TOE_DIST_XCHG": "allgather", "TOE_EXPECT_TRANSPORT": "nccl-allgather"})
+    assert r.returncode == 0 and "DIST PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -444,7 +444,7 @@ class Context:
     def comm_info(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         self._ck(self.lib.toe_comm_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"nranks": a.value, "rank": b.value, "transport": {0: "single-gpu", 1: "nccl", 2: "peer-memory"}[c.value]}
+        return {"nranks": a.value, "rank": b.value, "transport": {0: "single-gpu", 1: "nccl", 2: "peer-memory", 3: "nccl-allgather"}[c.value]}
 
     def local_sizes(self):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()

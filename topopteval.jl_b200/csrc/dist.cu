@@ -20,6 +20,7 @@ struct NcclApi {
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -34,7 +35,7 @@ static int nccl_load(std::string& err) {
     // tests/cuda_emu: rank threads of one process rendezvous through the stand-in functions (test infrastructure only)
     (void)err;
     g_nccl.GetUniqueId = &ncclGetUniqueId; g_nccl.CommInitRank = &ncclCommInitRank; g_nccl.CommDestroy = &ncclCommDestroy;
-    g_nccl.AllReduce = &ncclAllReduce; g_nccl.Send = &ncclSend; g_nccl.Recv = &ncclRecv; g_nccl.GroupStart = &ncclGroupStart;
+    g_nccl.AllReduce = &ncclAllReduce; g_nccl.AllGather = &ncclAllGather; g_nccl.Send = &ncclSend; g_nccl.Recv = &ncclRecv; g_nccl.GroupStart = &ncclGroupStart;
     g_nccl.GroupEnd = &ncclGroupEnd; g_nccl.GetErrorString = &ncclGetErrorString;
     g_nccl.h = (void*)&g_nccl;
     return TOE_OK;
@@ -44,7 +45,7 @@ static int nccl_load(std::string& err) {
     for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
     if (!h) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return TOE_ERR_COMM; }
 #define SYM(f) g_nccl.f = (decltype(g_nccl.f))dlsym(h, "nccl" #f); if (!g_nccl.f) { err = "libnccl lacks nccl" #f; return TOE_ERR_COMM; }
-    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllReduce) SYM(Send) SYM(Recv) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllReduce) SYM(AllGather) SYM(Send) SYM(Recv) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
 #undef SYM
     g_nccl.h = h;
     return TOE_OK;
@@ -88,9 +89,17 @@ struct DistState {
     u64 xseq = 0;                         // exchange sequence number (identical on all ranks)
     DevBuf<u64> gbar;                     // grid-barrier counter of the exchange kernel (monotonic)
     u64 xlaunch = 0;                      // launches of the exchange kernel so far (local)
+    // all-gather exchange (opt-in, TOE_DIST_XCHG=allgather): ONE collective per operator application carries every rank's packed
+    // interface values plus its two partial scalars; each rank picks its neighbours' segments out of the gathered buffer
+    bool ag_ok = false;
+    i64 ag_stride = 0;                    // doubles per rank in the gathered buffer: 3 * max_r(n_shared_total) + 2 (even → 16-byte slices)
+    DevBuf<double> ag_send, ag_recv;      // 2 x stride, 2 x nranks * stride (halves alternate like the p2p staging)
+    DevBuf<int> if_src_ag;                // unpack sources in gathered-buffer coordinates (node slots; -1 = own value)
 };
 
 static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host);
+static int allgather_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host);
+static int exchange_allgather(toe_ctx* ctx, double* y, double* scal, int count);
 
 bool dist_active(toe_ctx* ctx) { return ctx->dist != nullptr; }
 
@@ -419,6 +428,7 @@ int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, cons
     TRY(ensure_vectors(ctx));                       // the exchange kernel reads the PCG `done` flag
     CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
     TRY(mailbox_setup(ctx, d, if_src));
+    TRY(allgather_setup(ctx, d, if_src));
     TRY(dist_warm_up(ctx));
     return dist_align(ctx);
 }
@@ -464,7 +474,9 @@ static int dist_warm_up(toe_ctx* ctx) {
 
 int dist_post_spmv(toe_ctx* ctx, double* y) {
     DistState* d = ctx->dist;
-    if (!d || d->nranks == 1 || d->n_shared_total == 0 || !y) return TOE_OK;
+    if (!d || d->nranks == 1 || !y) return TOE_OK;
+    if (d->ag_ok) return exchange_allgather(ctx, y, nullptr, 0);      // a collective: also ranks without an interface take part
+    if (d->n_shared_total == 0) return TOE_OK;
     int n = d->n_shared_total;
     // the staging buffers alternate between two halves: an exchange never reuses the buffers of the previous one, whatever
     // the transport's completion semantics for the peer's side of a send/receive are
@@ -684,6 +696,96 @@ static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_
     return TOE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// All-gather exchange (opt-in: TOE_DIST_XCHG=allgather).  Interfaces are small (157 KB per neighbour at 10M tets / N=2), so
+// instead of a group of sends / receives plus an allreduce every rank contributes ONE slice — its packed interface values in
+// its own send layout, then its two partial scalars — to ONE ncclAllGather; the unpack kernel reads the neighbours' segments
+// straight out of the gathered buffer (offsets exchanged once per set-up) and sums the scalars in rank order.  Same arithmetic
+// and summation order as the other transports → bit-identical iterates.  3 launches per exchange instead of 4, and no
+// point-to-point traffic at all.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_pack_ag(const int* __restrict__ send_nodes, const double* __restrict__ y, const double* scal, int nscal,
+                          double* __restrict__ slice, int n, i64 stride) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n) { int s = i / 3, c = i - 3 * s; slice[i] = y[3 * (size_t)send_nodes[s] + c]; }
+    if (i < 2) slice[stride - 2 + i] = (i < nscal) ? scal[i] : 0.0;
+}
+__global__ void k_unpack_ag(const int* __restrict__ if_node, const int* __restrict__ if_ptr, const int* __restrict__ if_src_ag,
+                            const double* __restrict__ all, double* __restrict__ y, int n_if, double* scal, int nscal, int nranks, i64 stride) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && nscal > 0) {                                   // scalars in rank order: identical bits on every rank
+        double s0 = 0.0, s1 = 0.0;
+        for (int r = 0; r < nranks; r++) { s0 += all[(size_t)r * stride + stride - 2]; s1 += all[(size_t)r * stride + stride - 1]; }
+        scal[0] = s0; if (nscal > 1) scal[1] = s1;
+    }
+    if (i >= 3 * n_if) return;
+    int k = i / 3, c = i - 3 * k;
+    size_t dof = 3 * (size_t)if_node[k] + c;
+    double own = y[dof], s = 0.0;
+    for (int j = if_ptr[k]; j < if_ptr[k + 1]; j++) { int src = if_src_ag[j]; s += src < 0 ? own : all[3 * (size_t)src + c]; }   // ascending rank order
+    y[dof] = s;
+}
+
+// collective; called at every set-up.  Publishes, for every (rank r, peer q), where r's segment for q starts in r's send layout.
+static int allgather_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host) {
+    d->ag_ok = false;
+    const char* mode = getenv("TOE_DIST_XCHG");
+    if (d->nranks == 1 || !mode || strcmp(mode, "allgather") != 0 || d->p2p_ok) return TOE_OK;
+    const int R = d->nranks;
+    std::vector<int> tab((size_t)R * R + 1, 0);                  // own row: 1 + offset of the segment for peer q (0 = not a neighbour); last: max n_shared_total
+    for (size_t k = 0; k < d->nbr.size(); k++) tab[(size_t)d->rank * R + d->nbr[k]] = 1 + d->nbr_off[k];
+    DevBuf<int> dt; CU(dt.alloc(tab.size()));
+    CU(cudaMemcpyAsync(dt.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NC(g_nccl.AllReduce(dt.p, dt.p, (size_t)R * R, ncclInt, ncclSum, d->comm, ctx->stream));        // rows are disjoint: the sum is a gather
+    DevBuf<int> dm; CU(dm.alloc(2));
+    CU(cudaMemcpyAsync(dm.p, &d->n_shared_total, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NC(g_nccl.AllReduce(dm.p, dm.p, 1, ncclInt, ncclMax, d->comm, ctx->stream));
+    int gmax = 0;
+    CU(cudaMemcpyAsync(tab.data(), dt.p, (size_t)R * R * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&gmax, dm.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // per-rank slice: 3 * max_r(n_shared_total) interface doubles + 2 scalars, rounded up to a multiple of 6 doubles so that slices
+    // are 16-byte aligned AND start on a node slot (a source is then addressed by ONE int: node slot in the gathered buffer)
+    d->ag_stride = (3 * (i64)gmax + 2 + 5) / 6 * 6;
+    const i64 slots_per_rank = d->ag_stride / 3;
+    if ((i64)R * slots_per_rank > 2147483647LL / 4) return TOE_OK;        // would not fit the int indices: stay on send/recv
+    // source of my recv slot p (segment k of MY layout, position j) = slice of rank nbr[k], its segment for me, position j
+    std::vector<int> src(if_src_host.size());
+    const int nseg = (int)d->nbr.size();
+    for (size_t i = 0; i < if_src_host.size(); i++) {
+        const int p = if_src_host[i];
+        if (p < 0) { src[i] = -1; continue; }
+        int k = 0;
+        while (k + 1 < nseg && p >= d->nbr_off[k + 1]) k++;
+        const int r = d->nbr[k];
+        const int off_r = tab[(size_t)r * R + d->rank] - 1;
+        if (off_r < 0) return toe_fail(ctx, TOE_ERR_COMM, "all-gather exchange: rank %d does not list rank %d as a neighbour (interface maps disagree)", r, d->rank);
+        src[i] = (int)(r * slots_per_rank) + off_r + (p - d->nbr_off[k]);
+    }
+    CU(d->if_src_ag.alloc(src.size()));
+    if (!src.empty()) CU(cudaMemcpyAsync(d->if_src_ag.p, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(d->ag_send.alloc(2 * (size_t)d->ag_stride)); CU(d->ag_recv.alloc(2 * (size_t)R * d->ag_stride));
+    CU(cudaMemsetAsync(d->ag_send.p, 0, d->ag_send.bytes(), ctx->stream));       // slice padding travels: keep it defined
+    CU(cudaStreamSynchronize(ctx->stream));                                       // `src` (pageable) goes out of scope
+    d->ag_ok = true;
+    return TOE_OK;
+}
+
+static int exchange_allgather(toe_ctx* ctx, double* y, double* scal, int count) {
+    DistState* d = ctx->dist;
+    const int n = d->n_shared_total;
+    d->xpar ^= 1;
+    double* slice = d->ag_send.p + (size_t)d->xpar * d->ag_stride;
+    double* all = d->ag_recv.p + (size_t)d->xpar * d->nranks * d->ag_stride;
+    const i64 work = std::max<i64>(3 * (i64)n, 2);
+    LAUNCH(ctx, k_pack_ag, div_up(work, 256), 256, 0, (const int*)d->send_nodes.p, (const double*)y, (const double*)scal, count, slice, n, d->ag_stride);
+    NC(g_nccl.AllGather(slice, all, (size_t)d->ag_stride, ncclDouble, d->comm, ctx->stream));
+    const i64 work2 = std::max<i64>(3 * (i64)d->n_if, 1);
+    LAUNCH(ctx, k_unpack_ag, div_up(work2, 256), 256, 0, (const int*)d->if_node.p, (const int*)d->if_ptr.p, (const int*)d->if_src_ag.p,
+           (const double*)all, y, d->n_if, scal, count, d->nranks, d->ag_stride);
+    return TOE_OK;
+}
+
 // interface sum of y (grouped ncclSend/ncclRecv) followed by the allreduce of `count` scalars
 int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count) {
     DistState* d = ctx->dist;
@@ -699,6 +801,7 @@ int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count) {
                &ctx->cgs.p->done, ctx->errflag.p + 2, d->gbar.p, d->xlaunch++);
         return TOE_OK;
     }
+    if (d->ag_ok && count <= 2) return exchange_allgather(ctx, y, scal, count);
     int n = d->n_shared_total;
     d->xpar ^= 1;
     double* sb = d->sendbuf.p + (size_t)d->xpar * 3 * n;
@@ -848,6 +951,6 @@ int dist_info(toe_ctx* ctx, int* nranks, int* rank, int* transport) {
     DistState* d = ctx->dist;
     if (nranks) *nranks = d ? d->nranks : 1;
     if (rank) *rank = d ? d->rank : 0;
-    if (transport) *transport = (!d || d->nranks == 1) ? 0 : (d->p2p_ok ? 2 : 1);
+    if (transport) *transport = (!d || d->nranks == 1) ? 0 : (d->p2p_ok ? 2 : (d->ag_ok ? 3 : 1));
     return TOE_OK;
 }
