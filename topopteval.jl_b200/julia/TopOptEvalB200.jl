@@ -25,7 +25,7 @@ export setup_problem, create_material_model, create_simp_material_model,
        apply_fixed_boundary!, apply_sliding_boundary!, apply_force!,
        apply_volume_force!, apply_gravity!, apply_acceleration!, apply_variable_density_volume_force!,
        solve_system, solve_system_simp, solve_system_robust, solve_system_robust_simp, solve_system_adaptive,
-       calculate_stresses, calculate_stresses_simp,
+       calculate_stresses, calculate_stresses_simp, ferrite_dofhandler,
        SolverConfig, element_energies, compliance,
        select_nodes_by_plane, select_nodes_by_circle, get_node_dofs, get_boundary_facets, compute_boundary_area,
        apply_surface_traction!, apply_uniform_surface_traction!
@@ -53,8 +53,31 @@ struct B200DofHandler
     grid::Grid
     ndofs::Int
     node_first_dof::Vector{Int}      # 1-based, 0 = node in no cell  (what get_node_dofs :265-293 rebuilds per call)
+    ferrite::Base.RefValue{Any}      # the genuine Ferrite.DofHandler, built on first request (ferrite_dofhandler)
 end
+B200DofHandler(ctx, grid, ndofs, nfd) = B200DofHandler(ctx, grid, ndofs, nfd, Ref{Any}(nothing))
 Ferrite.ndofs(dh::B200DofHandler) = dh.ndofs
+
+"""
+    ferrite_dofhandler(dh::B200DofHandler) -> Ferrite.DofHandler
+
+The reference's own `DofHandler` for the same grid (`setup_problem`, FiniteElementAnalysis.jl:173-176), built lazily and cached.
+The GPU path numbers DOFs exactly as Ferrite's `close!` does (first touch in cell order), so `u` and `prescribed_dofs` index it
+directly.  Needed only where reference code dispatches on `Ferrite.DofHandler` — `ResultsExport.export_results(u, dh, file)`
+(ResultsExport.jl:25) and `export_boundary_conditions` — never on the hot path.
+"""
+function ferrite_dofhandler(dh::B200DofHandler)
+    if dh.ferrite[] === nothing
+        hex = typeof(getcells(dh.grid, 1)) <: Ferrite.Hexahedron
+        ip = hex ? Lagrange{RefHexahedron,1}()^3 : Lagrange{RefTetrahedron,1}()^3
+        fdh = DofHandler(dh.grid)
+        add!(fdh, :u, ip)
+        close!(fdh)
+        ndofs(fdh) == dh.ndofs || error("Ferrite numbers $(ndofs(fdh)) DOFs, the GPU path $(dh.ndofs)")
+        dh.ferrite[] = fdh
+    end
+    return dh.ferrite[]::DofHandler
+end
 
 struct B200CellValues; npc::Int; nqp::Int; end
 struct B200Matrix; ctx::Ctx; n::Int; nnz::Int; end          # K lives in HBM; materialise with sparse(K)
@@ -207,6 +230,8 @@ function Base.getindex(s::StressField, cell::Int)
     end
     return [SymmetricTensor{2,3}((v[1], v[4], v[6], v[2], v[5], v[3])) for v in eachcol(@view s.sigma[:, :, cell])]
 end
+"The reference's container: `Dict{Int64,Vector{SymmetricTensor{2,3}}}` (what `export_results(stress_field, dh, file)`, ResultsExport.jl:55, dispatches on)."
+Base.Dict(s::StressField) = Dict{Int64,Vector{SymmetricTensor{2,3,Float64,6}}}(c => s[c] for c in 1:s.ne)
 Base.length(s::StressField) = s.ne
 Base.haskey(s::StressField, cell::Int) = 1 <= cell <= s.ne
 Base.keys(s::StressField) = 1:s.ne
