@@ -44,9 +44,11 @@ def numpy_two_level_iterations(fo, pkg, pts, cells, boxes, tol):
     return k, x, fo.solve_direct(prob)
 
 
-def check_two_level(pkg, fo, ctx, cases, tol=1e-10):
+def check_two_level(pkg, fo, ctx, cases, tol=1e-10, auto_dims=(24, 8, 4), light_after_first=False):
+    """light_after_first (emulated runs, where a two-level iteration costs 25 ms): graph replay and the probing cross-check only on the first case"""
     try:
-        for dims, hexm, boxes, simp in cases:
+        for icase, (dims, hexm, boxes, simp) in enumerate(cases):
+            light = light_after_first and icase > 0
             os.environ["TOE_TL_BOXES"] = ",".join(map(str, boxes))
             pts, cells = pkg.meshgen.cantilever(*dims, hex=hexm)
             ctx.set_mesh(pts, cells); ctx.build_dofs(); ctx.build_pattern()
@@ -66,7 +68,7 @@ def check_two_level(pkg, fo, ctx, cases, tol=1e-10):
                 ctx.add_nodal_force(load, [0.0, 0.0, -1.0]); ctx.apply_dirichlet(pres)
                 s0 = ctx.solve_pcg(tol, tol, 100000, matrix_free=mf); u0 = ctx.solution()
                 runs = []
-                for graph in (False, True):
+                for graph in ((False,) if light else (False, True)):
                     s1 = ctx.solve_pcg(tol, tol, 100000, matrix_free=mf, two_level=True, graph=graph, history=True)
                     u1 = ctx.solution()
                     assert s1["converged"] == 1 and s1["breakdown"] == 0 and s1["coarse_dofs"] == 6 * int(np.prod(boxes))
@@ -76,8 +78,8 @@ def check_two_level(pkg, fo, ctx, cases, tol=1e-10):
                     res = s1["residuals"]
                     assert res.size == s1["niter"] + 1 and res[-1] <= tol + tol * res[0]
                     runs.append((s1["niter"], u1))
-                assert runs[0][0] == runs[1][0] and np.array_equal(runs[0][1], runs[1][1])          # graph replay = direct launches, bit for bit
-                if not mf:      # assembled K: the coarse operator comes straight from the blocks; the probing path must agree with it
+                assert light or (runs[0][0] == runs[1][0] and np.array_equal(runs[0][1], runs[1][1]))          # graph replay = direct launches, bit for bit
+                if not mf and not light:      # assembled K: the coarse operator comes straight from the blocks; the probing path must agree with it
                     os.environ["TOE_TL_PROBE"] = "1"
                     try:
                         if simp:
@@ -99,7 +101,7 @@ def check_two_level(pkg, fo, ctx, cases, tol=1e-10):
         # automatic box choice (no TOE_TL_BOXES): halve the longest box edge until ≥ target boxes
         os.environ.pop("TOE_TL_BOXES", None)
         os.environ["TOE_TL_BOXES_TARGET"] = "12"
-        pts, cells = pkg.meshgen.cantilever(24, 8, 4)
+        pts, cells = pkg.meshgen.cantilever(*auto_dims)
         ctx.set_mesh(pts, cells); ctx.build_dofs(); ctx.build_pattern()
         ctx.assemble_lame(*pkg.create_material_model(1.0, 0.3))
         fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0); load = pkg.meshgen.nodes_at_plane(pts, 0, 60.0)
