@@ -9,6 +9,7 @@
 #include <deque>
 #include <map>
 #include <memory>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -202,6 +203,12 @@ void run_block(Rank& r, unsigned b, unsigned T, size_t smem) {
     }
 }
 
+static int block_order_from_env() {
+    const char* e = getenv("EMU_BLOCKS");
+    return !e ? 0 : (!strcmp(e, "reverse") ? 1 : 2);
+}
+std::atomic<int> g_block_order{block_order_from_env()};
+
 void run_grid(Rank& r, unsigned grid, unsigned block, size_t smem, const std::function<void()>& body) {
     if (block == 0 || block > 1024) { r.last_error = cudaErrorInvalidValue; return; }
     if (smem > 227 * 1024) { r.last_error = cudaErrorInvalidValue; return; }
@@ -209,7 +216,21 @@ void run_grid(Rank& r, unsigned grid, unsigned block, size_t smem, const std::fu
     gridDim.x = grid; blockDim.x = block;
     r.body = &body;
     if (r.next_coresident) { r.next_coresident = false; run_grid_coresident(r, grid, block); }
-    else for (unsigned b = 0; b < grid && !r.deadlock; b++) run_block(r, b, block, smem);
+    else {
+        // EMU_BLOCKS=reverse | shuffle: the blocks of a grid run last-to-first / in a fresh pseudo-random order.  CUDA promises no block
+        // order, so every result must stay the same (bit for bit where the code claims determinism); a kernel in which some block
+        // silently relies on another block of the SAME launch having run (or not yet run) gives different answers here.
+        const int mode = g_block_order.load();                 // 0 forward, 1 reverse, 2 shuffle (EMU_BLOCKS or emu_set_block_order)
+        if (mode == 0) { for (unsigned b = 0; b < grid && !r.deadlock; b++) run_block(r, b, block, smem); }
+        else if (mode == 1) { for (unsigned b = grid; b-- > 0 && !r.deadlock;) run_block(r, b, block, smem); }
+        else {
+            static thread_local unsigned long long brng = 0x2545F4914F6CDD1DULL;
+            std::vector<unsigned> ord(grid);
+            for (unsigned b = 0; b < grid; b++) ord[b] = b;
+            for (unsigned b = grid; b > 1; b--) { brng = brng * 6364136223846793005ULL + 1442695040888963407ULL; std::swap(ord[b - 1], ord[(unsigned)((brng >> 33) % b)]); }
+            for (unsigned k = 0; k < grid && !r.deadlock; k++) run_block(r, ord[k], block, smem);
+        }
+    }
     r.body = nullptr; r.cur = -1;
     r.deadlock = false;
 }
@@ -219,6 +240,7 @@ namespace {
 std::mutex g_attr_mutex;
 std::map<const void*, int> g_max_dyn_smem;
 }
+extern "C" void emu_set_block_order(int mode) { g_block_order.store(mode); }
 extern "C" void emu_set_max_dyn_smem(const void* fn, int bytes) { std::lock_guard<std::mutex> lk(g_attr_mutex); g_max_dyn_smem[fn] = bytes; }
 extern "C" void emu_misaligned(const void* p, unsigned bytes) {
     fprintf(stderr, "cuda_emu: MISALIGNED %u-byte load at %p\n", bytes, p);

@@ -193,3 +193,24 @@ def test_two_level_preconditioner_on_partitions(emu, world, dims, simp, mf, monk
         assert np.linalg.norm(r["u"] - ref["u"]) <= 1e-8 * np.linalg.norm(ref["u"])
         assert np.linalg.norm(r["u"] - ref_j["u"]) <= 1e-8 * np.linalg.norm(ref_j["u"])
         assert abs(r["e"] - ref["e"]) <= 1e-8 * abs(ref["e"])
+
+
+def test_partitioned_results_do_not_depend_on_block_order(emu):
+    """the partitioned path (single-reduction CG, pack / unpack, partition set-up kernels) under first-to-last, last-to-first and
+    shuffled block execution: bit-identical solves — no kernel leans on the order in which the blocks of a launch happen to run"""
+    pkg, lib = emu
+    prob = _problem(pkg, (10, 4, 2), True)
+    try:
+        lib.emu_set_block_order(0)
+        ref = _run_ranks(pkg, 2, prob, False, repeats=1, tol=1e-9)
+        for mode in (1, 2):
+            lib.emu_set_block_order(mode)
+            got = _run_ranks(pkg, 2, prob, False, repeats=1, tol=1e-9)
+            for rk in range(2):
+                a, b = ref[rk][0], got[rk][0]
+                assert a["it"] == b["it"] and b["conv"] == 1 and b["restarts"] == 0, (mode, rk, a["it"], b["it"])
+                for key in ("u", "f", "diag", "ee", "vm", "nfd"):
+                    assert np.array_equal(a[key], b[key]), (mode, rk, key)
+                assert np.array_equal(ref[rk][-1]["part"], got[rk][-1]["part"])
+    finally:
+        lib.emu_set_block_order(0)

@@ -115,3 +115,52 @@ def test_many_contexts_come_and_go(emu):
         ctx.assemble_lame(0.5, 0.4)
         ctx.close()
     assert lib.emu_live_allocations() == base
+
+
+def test_results_do_not_depend_on_block_order(emu):
+    """CUDA promises no order among the blocks of a launch.  The emulated build runs them first-to-last, last-to-first and in a
+    shuffled order: everything the library calls deterministic (K, loads, PCG iterates of both operator forms and of the two-level
+    preconditioner, energies, stresses) must come out bit-identical — a kernel in which a block leans on another block of the same
+    launch having run already (or not yet) fails here."""
+    pkg, lib = emu
+    A = pkg._lib
+    pts, cells = pkg.meshgen.cantilever(7, 3, 2)
+    rho = pkg.meshgen.simp_like_density(cells.shape[0])
+    fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0); load = pkg.meshgen.nodes_at_plane(pts, 0, 60.0)
+
+    def run():
+        ctx = pkg.Context(0)
+        out = {}
+        ctx.set_mesh(pts, cells); ctx.build_dofs(); ctx.build_pattern()
+        nfd = ctx.node_dofs()
+        pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
+        out["pattern"] = np.concatenate(ctx.pattern())
+        for name, variant in (("gather", A.ASM_GATHER), ("rows", A.ASM_ROWS)):
+            ctx.assemble_simp(1.0, 0.3, 1e-8, 3.0, rho, variant)
+            out["K_" + name] = ctx.values()
+        ctx.assemble_simp(1.0, 0.3, 1e-8, 3.0, rho)
+        ctx.add_nodal_force(load, [0.0, 0.0, -1.0])
+        ctx.add_volume_force([0.0, 0.0, -0.01], density=rho, skip_below=1e-6)
+        out["m"] = ctx.apply_dirichlet(pres)
+        out["f"] = ctx.rhs()
+        for key, kw in (("asm", {}), ("mf", {"matrix_free": True}), ("tl", {"two_level": True})):
+            st = ctx.solve_pcg(1e-9, 1e-9, 20000, **kw)
+            assert st["converged"] == 1
+            out["u_" + key] = ctx.solution(); out["it_" + key] = st["niter"]
+        e, c, ee = ctx.energy(per_element=True)
+        sig, vm, mx, arg = ctx.stresses(True, True)
+        out.update(e=e, c=c, ee=ee, sig=sig, vm=vm, mx=mx, arg=arg)
+        ctx.close()
+        return out
+
+    lib.emu_set_block_order(0)
+    try:
+        ref = run()
+        for mode in (1, 2):
+            lib.emu_set_block_order(mode)
+            r = run()
+            for k, v in ref.items():
+                same = np.array_equal(v, r[k]) if isinstance(v, np.ndarray) else v == r[k]
+                assert same, "block order %d changes %s" % (mode, k)
+    finally:
+        lib.emu_set_block_order(0)
