@@ -141,6 +141,9 @@ def test_results_do_not_depend_on_block_order(emu):
         ctx.assemble_simp(1.0, 0.3, 1e-8, 3.0, rho)
         ctx.add_nodal_force(load, [0.0, 0.0, -1.0])
         ctx.add_volume_force([0.0, 0.0, -0.01], density=rho, skip_below=1e-6)
+        facets = ctx.boundary_facets(ctx.surface_nodes())                      # the whole skin: every surface node collects several facets
+        ctx.add_surface_traction(facets, traction_uniform=[0.3, -0.2, -0.5])
+        out["facets"] = np.asarray(facets)
         out["m"] = ctx.apply_dirichlet(pres)
         out["f"] = ctx.rhs()
         for key, kw in (("asm", {}), ("mf", {"matrix_free": True}), ("tl", {"two_level": True})):

@@ -107,20 +107,23 @@ __global__ void k_compact_facets(const int* __restrict__ flag, const int* __rest
     out[2 * (size_t)pos[t]] = t / NF + 1; out[2 * (size_t)pos[t] + 1] = t % NF + 1;
 }
 
-// one thread per facet: quadrature points, dΓ and — when f != null — the load Σ_q N_a t(x_q) dΓ_q scattered to the face nodes.
+// one thread per facet: quadrature points, dΓ and — when vload != null — the loads Σ_q N_a t(x_q) dΓ_q of its vertices, left in
+// vload[(i*4+k)*3+c] with the vertex's dof-node in vnode[i*4+k] (-1: none); k_vertex_loads_to_f adds them up in a fixed order.
 // traction: per-qp values t_qp (3 per point) or, if null, the uniform vector (tx,ty,tz).
 template <int NPC>
 __global__ void k_facets(const int64_t* __restrict__ facets, i64 nf, const int* __restrict__ conn0, const double* __restrict__ xyz, i64 ne,
                          const int* __restrict__ node_q, double* __restrict__ xq_out, double* __restrict__ dg_out,
-                         const double* __restrict__ t_qp, double tx, double ty, double tz, double* f,
+                         const double* __restrict__ t_qp, double tx, double ty, double tz, double* __restrict__ vload, int* __restrict__ vnode,
                          double* __restrict__ area_part, double* __restrict__ force_part, int* err) {
     const int FN = NPC == 4 ? 3 : 4, NQP = NPC == 4 ? 3 : 4, NF = NPC == 4 ? 4 : 6;
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nf) return;
     const int64_t e = facets[2 * i] - 1, fid = facets[2 * i + 1] - 1;
     double area = 0.0, tot[3] = {0, 0, 0};
-    if (e < 0 || e >= ne || fid < 0 || fid >= NF) { atomicExch(err + 2, 1); }
-    else {
+    if (e < 0 || e >= ne || fid < 0 || fid >= NF) {
+        atomicExch(err + 2, 1);
+        if (vload) { for (int k = 0; k < 4; k++) vnode[4 * i + k] = -1; }
+    } else {
         int g[4]; double P[4][3];
 #pragma unroll
         for (int k = 0; k < FN; k++) {
@@ -159,7 +162,7 @@ __global__ void k_facets(const int64_t* __restrict__ facets, i64 nf, const int* 
             if (xq_out) { for (int c = 0; c < 3; c++) xq_out[((size_t)i * NQP + q) * 3 + c] = x[c]; }
             if (dg_out) dg_out[(size_t)i * NQP + q] = dg;
             area += dg;
-            if (f) {
+            if (vload) {
                 double t3[3] = {tx, ty, tz};
                 if (t_qp) { for (int c = 0; c < 3; c++) t3[c] = t_qp[((size_t)i * NQP + q) * 3 + c]; }
 #pragma unroll
@@ -170,16 +173,44 @@ __global__ void k_facets(const int64_t* __restrict__ facets, i64 nf, const int* 
                 for (int c = 0; c < 3; c++) tot[c] += t3[c] * dg;
             }
         }
-        if (f) {
-            for (int k = 0; k < FN; k++) {
-                const int qn = node_q[g[k]];
-                if (qn < 0) continue;
-                for (int c = 0; c < 3; c++) atomicAdd(&f[3 * (size_t)qn + c], load[k][c]);
+        if (vload) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                vnode[4 * i + k] = k < FN ? node_q[g[k < FN ? k : 0]] : -1;
+#pragma unroll
+                for (int c = 0; c < 3; c++) vload[(4 * (size_t)i + k) * 3 + c] = load[k][c];
             }
         }
     }
     area_part[i] = area;
     if (force_part) { force_part[3 * i] = tot[0]; force_part[3 * i + 1] = tot[1]; force_part[3 * i + 2] = tot[2]; }
+}
+
+// Deterministic scatter of the per-vertex loads: vertex entries (facet*4+k) are grouped by dof-node with a counting sort (integer
+// atomics only), every node's short list is put in ascending entry order, and ONE thread per node adds its entries to f in that
+// order — the sum the reference forms facet by facet in list order, bit-reproducible from run to run (no floating-point atomics).
+__global__ void k_vl_count(const int* __restrict__ vnode, i64 nent, int* cnt) {
+    i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nent && vnode[t] >= 0) atomicAdd(&cnt[vnode[t]], 1);
+}
+__global__ void k_vl_fill(const int* __restrict__ vnode, i64 nent, const int* __restrict__ ptr, int* cursor, int* __restrict__ list) {
+    i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nent) return;
+    const int q = vnode[t];
+    if (q >= 0) list[ptr[q] + atomicAdd(&cursor[q], 1)] = (int)t;
+}
+__global__ void k_vertex_loads_to_f(const int* __restrict__ ptr, int* __restrict__ list, const double* __restrict__ vload, double* __restrict__ f, int nq) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int lo = ptr[q], hi = ptr[q + 1];
+    if (lo == hi) return;
+    for (int i = lo + 1; i < hi; i++) { int v = list[i], j = i - 1; while (j >= lo && list[j] > v) { list[j + 1] = list[j]; j--; } list[j + 1] = v; }
+    double s[3] = {f[3 * (size_t)q], f[3 * (size_t)q + 1], f[3 * (size_t)q + 2]};
+    for (int i = lo; i < hi; i++) {
+        const double* l = vload + 3 * (size_t)list[i];
+        s[0] += l[0]; s[1] += l[1]; s[2] += l[2];
+    }
+    f[3 * (size_t)q] = s[0]; f[3 * (size_t)q + 1] = s[1]; f[3 * (size_t)q + 2] = s[2];
 }
 
 // fixed-order sum of n values with stride `stride` (one block)
@@ -291,14 +322,32 @@ int facet_integrals(toe_ctx* ctx, const int64_t* facets, i64 nf, double* xq_out,
     if (dg_out) CU(dg.alloc((size_t)nqp * nf));
     if (add_load && t_qp) { CU(tq.alloc((size_t)3 * nqp * nf)); CU(cudaMemcpyAsync(tq.p, t_qp, (size_t)3 * nqp * nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); }
     CU(apart.alloc(nf + 4)); CU(fpart.alloc(3 * nf + 4));
+    DevBuf<double> vload; DevBuf<int> vnode;
+    if (add_load) {
+        if (4 * nf > 2147483647LL) return toe_fail(ctx, TOE_ERR_ARG, "surface traction: too many facets (%lld)", (long long)nf);
+        CU(vload.alloc((size_t)12 * nf)); CU(vnode.alloc((size_t)4 * nf));
+    }
     CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
     const double tu[3] = {t_uniform ? t_uniform[0] : 0.0, t_uniform ? t_uniform[1] : 0.0, t_uniform ? t_uniform[2] : 0.0};
 #define FACET_ARGS (const int64_t*)d.p, nf, (const int*)ctx->conn0.p, (const double*)ctx->xyz.p, ctx->ne, (const int*)ctx->node_q.p, xq_out ? xq.p : (double*)nullptr, \
-        dg_out ? dg.p : (double*)nullptr, (add_load && t_qp) ? (const double*)tq.p : (const double*)nullptr, tu[0], tu[1], tu[2], add_load ? ctx->f.p : (double*)nullptr, \
+        dg_out ? dg.p : (double*)nullptr, (add_load && t_qp) ? (const double*)tq.p : (const double*)nullptr, tu[0], tu[1], tu[2], add_load ? vload.p : (double*)nullptr, add_load ? vnode.p : (int*)nullptr, \
         apart.p, fpart.p, ctx->errflag.p
     if (ctx->npc == 4) LAUNCH(ctx, k_facets<4>, div_up(nf, 128), 128, 0, FACET_ARGS);
     else               LAUNCH(ctx, k_facets<8>, div_up(nf, 128), 128, 0, FACET_ARGS);
 #undef FACET_ARGS
+    DevBuf<int> vptr, vcur, vlist;
+    if (add_load) {
+        const i64 nent = 4 * nf;
+        const int nq = ctx->nq;
+        CU(vptr.alloc((size_t)nq + 1)); CU(vcur.alloc((size_t)nq + 1)); CU(vlist.alloc((size_t)nent));
+        CU(cudaMemsetAsync(vptr.p, 0, ((size_t)nq + 1) * sizeof(int), ctx->stream));
+        CU(cudaMemsetAsync(vcur.p, 0, ((size_t)nq + 1) * sizeof(int), ctx->stream));
+        LAUNCH(ctx, k_vl_count, div_up(nent, 256), 256, 0, (const int*)vnode.p, nent, vptr.p);
+        i64 tot_ent = 0;
+        TRY(scan_exclusive_i32(ctx, vptr.p, vptr.p, nq, &tot_ent));
+        LAUNCH(ctx, k_vl_fill, div_up(nent, 256), 256, 0, (const int*)vnode.p, nent, (const int*)vptr.p, vcur.p, vlist.p);
+        LAUNCH(ctx, k_vertex_loads_to_f, div_up(nq, 128), 128, 0, (const int*)vptr.p, vlist.p, (const double*)vload.p, ctx->f.p, nq);
+    }
     LAUNCH(ctx, k_sum_fixed, 1, 256, 0, (const double*)apart.p, nf, 1, apart.p + nf);
     for (int c = 0; c < 3; c++) LAUNCH(ctx, k_sum_fixed, 1, 256, 0, (const double*)(fpart.p + c), nf, 3, fpart.p + 3 * nf + c);
     double h[4] = {0, 0, 0, 0}; int e = 0;
