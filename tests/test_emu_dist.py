@@ -150,7 +150,7 @@ def test_peer_memory_exchange_protocol(emu, world, dims, monkeypatch):
             assert r["it"] == nccl[rk][0]["it"] and np.array_equal(r["u"], nccl[rk][0]["u"]), (rk, rep, r["it"], nccl[rk][0]["it"])
 
 
-@pytest.mark.parametrize("world,dims,simp,mf", [(2, (10, 4, 3), False, True), (4, (12, 5, 3), True, False), (8, (16, 4, 2), False, False)])
+@pytest.mark.parametrize("world,dims,simp,mf", [(2, (10, 4, 3), False, True), (4, (10, 4, 2), True, False), (8, (16, 4, 2), False, False)])
 def test_allgather_exchange_transport(emu, world, dims, simp, mf, monkeypatch):
     """TOE_DIST_XCHG=allgather: one ncclAllGather per exchange carries every rank's packed interface values and its partial scalars.
     Same arithmetic and summation order as the send/recv transport → bit-identical iterates, loads, diagonals and per-cell outputs;
@@ -203,7 +203,7 @@ def test_partitioned_results_do_not_depend_on_block_order(emu):
     try:
         lib.emu_set_block_order(0)
         ref = _run_ranks(pkg, 2, prob, False, repeats=1, tol=1e-9)
-        for mode in (1, 2):
+        for mode in (2, 1)[:1 if os.environ.get("TOE_EMU_FULL") != "1" else 2]:      # shuffled (and, on request, last-to-first)
             lib.emu_set_block_order(mode)
             got = _run_ranks(pkg, 2, prob, False, repeats=1, tol=1e-9)
             for rk in range(2):
