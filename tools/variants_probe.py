@@ -52,6 +52,18 @@ def main():
         out["assembly"] = asm
     # ---- matrix-free operator variants ----------------------------------------------------------------------------
     ctx.assemble_lame(lam, mu)
+    # bit-identity of the pipelined operator is checked BEFORE constraints exist: with prescribed DOFs toe_spmv masks the input
+    # columns, and the masking form always takes the tile kernel (the pipelined kernel serves the PCG loop, whose vectors are masked)
+    pipe_identical = None
+    if only in (None, "ebe"):
+        xf = np.random.default_rng(2).standard_normal(ctx.ndofs)
+        os.environ.pop("TOE_EBE_PIPE", None)
+        y0 = ctx.spmv(xf, matrix_free=True)
+        os.environ["TOE_EBE_PIPE"] = "1"
+        y1 = ctx.spmv(xf, matrix_free=True)
+        os.environ.pop("TOE_EBE_PIPE", None)
+        pipe_identical = bool(np.array_equal(y0, y1))
+        del xf, y0, y1
     load = pkg.meshgen.nodes_at_plane(pts, 0, 60.0); fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0)
     ctx.add_nodal_force(load, [0, 0, -1.0])
     nfd = ctx.node_dofs()
@@ -66,10 +78,7 @@ def main():
         else:
             os.environ.pop("TOE_EBE_PIPE", None)
         s, b = ctx.time_spmv(matrix_free=True, reps=20)
-        y = ctx.spmv(x, matrix_free=True)
-        if y_tile is None:
-            y_tile = y
-        ebe[name] = {"ms": s * 1e3, "GBs_algorithmic": b / s / 1e9, "bit_identical_to_tile": bool(np.array_equal(y, y_tile))}
+        ebe[name] = {"ms": s * 1e3, "GBs_algorithmic": b / s / 1e9, "bit_identical_to_tile": True if name == "tile" else pipe_identical}
     os.environ.pop("TOE_EBE_PIPE", None)
     if ebe:
         s, b = ctx.time_spmv(matrix_free=False, reps=20)
