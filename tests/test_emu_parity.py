@@ -46,12 +46,16 @@ def _adopt(name, slow=False):
 for _n in ["test_dofs_and_pattern_bit_exact", "test_dofs_permuted_cells_and_unreferenced_nodes", "test_ke_tet_fixture", "test_ke_hex_simp_fixture",
            "test_ke_partial_range_and_errors", "test_assembled_K_tet", "test_assembled_K_hex_simp", "test_gather_assembly_is_deterministic_and_symmetric",
            "test_per_cell_lame_matches_simp", "test_loads", "test_volume_force_tet", "test_dirichlet_ferrite_semantics", "test_spmv_assembled_and_matrix_free",
-           "test_stresses", "test_calculate_stresses_free_functions", "test_error_behaviour", "test_edge_single_cell_and_trivial_solves", "test_edge_duplicate_load_nodes_and_repeated_solves",
+           "test_stresses", "test_error_behaviour", "test_edge_single_cell_and_trivial_solves", "test_edge_duplicate_load_nodes_and_repeated_solves",
            "test_edge_sliding_boundary_and_void_material", "test_edge_arbitrary_material_callable"]:
     _adopt(_n)
 for _n in ["test_synthetic_cantilever_energies", "test_solve_c1_tet_beam", "test_pcg_krylov_semantics_and_iteration_count", "test_solve_c2_hex_simp", "test_runtests_recipe_linear_beam",
            "test_runtests_recipe_simp_beam", "test_gravity_cantilever_known_answer"]:
     _adopt(_n, slow=True)
+
+
+def test_calculate_stresses_free_functions(ctx, pkg, fo, golden_c1, golden_c2):
+    gp.check_calculate_stresses_free_functions(ctx, pkg, fo, golden_c1, golden_c2)
 
 
 def test_rows_assembly_variant(ctx, pkg, fo, golden_c1):

@@ -367,7 +367,7 @@ def test_stresses(ctx, pkg, fo, golden_c1, golden_c2):
         assert arg == argref == int(g["max_stress_cell"]) and abs(mx - float(g["max_von_mises"])) <= 1e-9 * mx
 
 
-def test_calculate_stresses_free_functions(ctx, pkg, fo, golden_c1, golden_c2):
+def check_calculate_stresses_free_functions(ctx, pkg, fo, golden_c1, golden_c2):      # run by test_gpu_zz_optin_variants.py (child process) and by the emulated suite
     """calculate_stresses(u, dh, cv, λ, μ) / calculate_stresses_simp(u, dh, cv, model, ρ) are free functions in the reference
     (FiniteElementAnalysis.jl:440 / :730): any u, any material — and the ctx's own K, material and solution are not touched."""
     def s6_of(sref):

@@ -24,10 +24,11 @@ import __graft_entry__ as graft
 pkg = graft.load_package()
 from oracle import fea_oracle as fo
 golden_c1 = dict(np.load(os.path.join(%r, "golden", "c1_tet_beam.npz")))
+golden_c2 = dict(np.load(os.path.join(%r, "golden", "c2_hex_simp.npz")))
 if os.environ.get("TOE_TEST_EMU") == "1":      # dry run of this file's plumbing where there is no GPU (tests/cuda_emu, test infrastructure)
     import emu_support
     pkg._lib._lib = emu_support.load_emu()[1]
-""" % (ROOT, TESTS, TESTS)
+""" % (ROOT, TESTS, TESTS, TESTS)
 
 
 def run_isolated(body, timeout):
@@ -40,6 +41,18 @@ def run_isolated(body, timeout):
         raise AssertionError("child exceeded %d s (hang?)\n%s" % (timeout, out[-2000:]))
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0 and "ISOLATED-OK" in r.stdout, "rc=%d\n%s\n%s" % (r.returncode, r.stdout[-3000:], r.stderr[-3000:])
+
+
+def test_calculate_stresses_free_functions():
+    """calculate_stresses / calculate_stresses_simp as the reference's free functions (any u, any material, ctx untouched): new C-ABI
+    entry points over the measured k_stress kernel"""
+    run_isolated("""
+        import pytest
+        import test_gpu_parity as gp
+        ctx = pkg.Context(0)
+        gp.check_calculate_stresses_free_functions(ctx, pkg, fo, golden_c1, golden_c2)
+        ctx.close()
+    """, 300)
 
 
 def test_rows_variant():
