@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE (see tests/emu_support.py): checks the logic of the partitioned path — RCB partition, interface maps,
 sub-assembled K, owner-masked dots, single-reduction CG recurrence, gathers back to the reference's DOF order — against the
-single-ctx result, with 0xFF-filled allocations so that any read-before-write shows.  The real gate is tests/test_dist.py on
+single-ctx result, with 0xFF-filled allocations so that any read-before-write shows.  The real gate is tests/test_gpu_y_dist.py on
 2/4 B200s."""
 import os
 import sys

@@ -1,5 +1,5 @@
 """The opt-in all-gather exchange transport (TOE_DIST_XCHG=allgather) on real GPUs: same parity bars as the default send/recv
-transport (tests/test_dist.py), through tests/dist_worker.py under torchrun.  Written after the round-1 GPU budget was spent
+transport (tests/test_gpu_y_dist.py), through tests/dist_worker.py under torchrun.  Written after the round-1 GPU budget was spent
 (bit-identical to send/recv on the emulated build), hence the last-sorting file name; skipped when fewer than 2 GPUs are visible."""
 import pytest
 
