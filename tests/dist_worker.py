@@ -57,7 +57,7 @@ def main():
         u = ctx.solution()
         e, c, ee = ctx.energy(per_element=True)
         _, vm, mx, arg = ctx.stresses(False, True)
-        return dict(u=u, e=e, c=c, ee=ee, it=st["niter"], conv=st["converged"], m=m, f=ctx.rhs(), nfd=nfd, mx=mx, arg=arg, vm=vm,
+        return dict(u=u, e=e, c=c, ee=ee, it=st["niter"], conv=st["converged"], restarts=st.get("restarts", 0), m=m, f=ctx.rhs(), nfd=nfd, mx=mx, arg=arg, vm=vm,
                     diag=ctx.diagonal())
 
     ctx = pkg.parallel.create_distributed_context(dist, local_rank)
@@ -94,8 +94,8 @@ def main():
             rel_ee = np.max(np.abs(r["ee"] - ref["ee"])) / np.max(np.abs(ref["ee"]))
             rel_f = np.max(np.abs(r["f"] - ref["f"])) / np.max(np.abs(ref["f"]))
             rel_d = np.max(np.abs(r["diag"] - ref["diag"]) / np.abs(ref["diag"]))
-            print("mf=%d iters %d (single %d) rel_u %.2e rel_e %.2e rel_c %.2e rel_ee %.2e rel_f %.2e rel_diag %.2e m %.12g/%.12g argmax %d/%d"
-                  % (mf, r["it"], ref["it"], rel_u, rel_e, rel_c, rel_ee, rel_f, rel_d, r["m"], ref["m"], r["arg"], ref["arg"]))
+            print("mf=%d iters %d (single %d) rel_u %.2e rel_e %.2e rel_c %.2e rel_ee %.2e rel_f %.2e rel_diag %.2e m %.12g/%.12g argmax %d/%d restarts %d"
+                  % (mf, r["it"], ref["it"], rel_u, rel_e, rel_c, rel_ee, rel_f, rel_d, r["m"], ref["m"], r["arg"], ref["arg"], r["restarts"]))
             good = (r["conv"] == 1 and rel_u < 1e-8 and rel_e < 1e-8 and rel_c < 1e-8 and rel_ee < 1e-8 and rel_f < 1e-12 and rel_d < 1e-12
                     and abs(r["m"] - ref["m"]) < 1e-12 * ref["m"] and np.array_equal(r["nfd"], ref["nfd"])
                     and abs(r["it"] - ref["it"]) <= max(5, ref["it"] // 50) and r["arg"] == ref["arg"]
