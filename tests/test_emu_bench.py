@@ -52,3 +52,26 @@ def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
     assert (d["stages"]["variants"] is None) == mf
     tl = d["stages"]["two_level_preconditioner"]
     assert (mf and tl is None) or "error" not in tl and tl["converged"] and tl["pcg_iterations"] < d["stages"]["pcg_iterations"] and tl["energy_rel_diff_vs_jacobi"] < 1e-6
+
+
+@pytest.mark.parametrize("section,key", [("asm", "assembly"), ("ebe", "matrix_free_operator")])
+def test_variants_probe_sections_on_emulated_build(monkeypatch, capsys, section, key):
+    """tools/variants_probe.py --only <section> (the child processes of bench.py's stages.variants) driven in-process on the emulated
+    build: the tool itself has no CPU route — the library handle is swapped here, by the test."""
+    import importlib.util
+    pkg, lib = emu_support.load_emu()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("variants_probe_under_test", os.path.join(root, "tools", "variants_probe.py"))
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.setattr(sys, "argv", ["variants_probe.py", "toy", "--only", section])
+    monkeypatch.chdir(root)
+    with emu_support.emulated(pkg, lib):
+        spec.loader.exec_module(mod)
+        capsys.readouterr()
+        mod.main()
+    out = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
+    assert key in out and out["ne"] == 288
+    if section == "asm":
+        assert out[key]["rows"]["max_rel_diff_Kx_vs_gather"] < 1e-13 and out[key]["rows"]["ms_min"] > 0
+    else:
+        assert out[key]["pipe"]["bit_identical_to_tile"] is True and out[key]["pipe"]["ms"] > 0

@@ -14,10 +14,6 @@ import __graft_entry__ as graft
 
 pkg = graft.load_package()
 A = pkg._lib
-if os.environ.get("TOE_TEST_EMU") == "1":          # dry run of this tool's plumbing where there is no GPU (tests/cuda_emu: never a measurement)
-    sys.path.insert(0, "tests")
-    import emu_support
-    pkg._lib._lib = emu_support.load_emu()[1]
 
 
 def main():
