@@ -49,3 +49,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".jl")):
                 src = open(os.path.join(dp, f)).read()
                 assert "fea_oracle" not in src and "oracle/" not in src and "import oracle" not in src, f
+
+
+def test_product_library_holds_no_emulation_code():
+    """the host-side emulation of the CUDA sources (tests/cuda_emu) is compiled from `#ifdef TOE_EMU` sections that the product
+    build never defines: libtopopt_b200.so exports no emu_* symbol, and neither bench.py nor tools/ nor the package can load the
+    emulated library (only tests/emu_support.py does)"""
+    so = os.path.join(ROOT, "topopteval.jl_b200", "libtopopt_b200.so")
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    assert "emu_" not in syms and " T toe_create" in syms
+    for path in [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + \
+                [os.path.join(dp, f) for top in ("tools", "topopteval.jl_b200") for dp, _, fs in os.walk(os.path.join(ROOT, top)) for f in fs
+                 if f.endswith((".py", ".sh", ".jl"))]:
+        src = open(path).read()
+        assert "emu_support" not in src and "libtopopt_emu" not in src, path
