@@ -63,3 +63,24 @@ def test_product_library_holds_no_emulation_code():
                  if f.endswith((".py", ".sh", ".jl"))]:
         src = open(path).read()
         assert "emu_support" not in src and "libtopopt_emu" not in src, path
+
+
+def test_header_is_plain_c_and_the_c_example_builds(tmp_path, have_gpu):
+    """include/topopt_b200.h is the drop-in boundary for hosts in any language: it must compile as strict C99 and as C++, and
+    examples/cantilever.c (the hot path through the C ABI alone) must build against the product library; without a GPU the
+    program refuses loudly."""
+    hdr = os.path.join(ROOT, "include", "topopt_b200.h")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "%s"\nint main(void) { return toe_version() == 0; }\n' % hdr)
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(src)],
+                ["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", str(src)]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    libdir = os.path.join(ROOT, "topopteval.jl_b200")
+    exe = tmp_path / "cantilever"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O1", os.path.join(ROOT, "examples", "cantilever.c"), "-I" + os.path.join(ROOT, "include"),
+                        "-L" + libdir, "-ltopopt_b200", "-Wl,-rpath," + libdir, "-lm", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if not have_gpu:
+        r = subprocess.run([str(exe), "4", "2", "1"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr

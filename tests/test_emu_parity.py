@@ -83,3 +83,34 @@ def test_boundary_selection_and_surface_traction(pkg, fo, golden_c1):
 def test_two_level_preconditioner(ctx, pkg, fo):
     import two_level_checks as tc
     tc.check_two_level(pkg, fo, ctx, [((8, 3, 2), False, (4, 2, 1), False), ((5, 2, 2), False, (3, 2, 2), True), ((5, 3, 2), True, (3, 1, 1), False)], auto_dims=(12, 4, 2), light_after_first=True)
+
+
+def test_c_example_against_the_oracle(emu, fo, tmp_path):
+    """examples/cantilever.c (plain C99 host, C ABI only) linked against the EMULATED library: the energy it prints equals the oracle's
+    direct solve of the same structured mesh — the C call sequence, its 1-based ids and its mesh generator are right."""
+    import re
+    import subprocess
+    pkg, lib = emu
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(emu_support.EMU_LIB)
+    exe = tmp_path / "cantilever_emu"
+    r = subprocess.run(["gcc", "-std=c99", "-O1", os.path.join(root, "examples", "cantilever.c"), "-I" + os.path.join(root, "include"),
+                        "-L" + libdir, "-ltopopt_emu", "-Wl,-rpath," + libdir, "-lm", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"} if not emu_support.ASAN else dict(os.environ)
+    r = subprocess.run([str(exe), "8", "3", "2"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"(\d+) tets, (\d+) DOFs, nnz (\d+) .* deformation energy ([0-9.eE+-]+), compliance ([0-9.eE+-]+), max von Mises ([0-9.eE+-]+) in cell (\d+)", r.stdout)
+    assert m, r.stdout
+    pts, cells = pkg.meshgen.cantilever(8, 3, 2)
+    prob = fo.setup_problem(pts, cells)
+    lam, mu = fo.create_material_model(1.0, 0.3)
+    fo.assemble_stiffness_matrix(prob, lam, mu)
+    fo.apply_force(prob, pkg.meshgen.nodes_at_plane(pts, 0, 60.0), [0.0, 0.0, -1.0])
+    fo.apply_dirichlet(prob, fo.fixed_boundary_dofs(prob, pkg.meshgen.nodes_at_plane(pts, 0, 0.0)))
+    u = fo.solve_direct(prob)
+    e_ref = fo.deformation_energy(prob, u)
+    _, _, mx_ref, arg_ref = fo.calculate_stresses(prob, u, lam, mu)
+    assert (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (cells.shape[0], prob.ndofs, prob.nnz)
+    assert abs(float(m.group(4)) - e_ref) <= 1e-6 * e_ref and abs(float(m.group(5)) - 2 * e_ref) <= 1e-6 * 2 * e_ref
+    assert abs(float(m.group(6)) - mx_ref) <= 1e-5 * mx_ref and int(m.group(7)) == arg_ref
