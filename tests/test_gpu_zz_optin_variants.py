@@ -122,3 +122,24 @@ def test_two_level_preconditioner_1m_tets():
         assert abs(st["niter"] - k_ref) <= max(10, k_ref // 5), (st["niter"], k_ref)
         ctx.close()
     """, 600)
+
+
+def test_c_host_example_reproduces_the_golden_energy(tmp_path):
+    """examples/cantilever.c — a plain C99 host, C ABI only — on the 24x8x4-cube cantilever: energy / compliance / sizes of the frozen
+    oracle fixture (tests/golden/synthetic_tet.npz).  A separate process by construction."""
+    import re
+
+    import numpy as np
+    g = np.load(os.path.join(TESTS, "golden", "synthetic_tet.npz"))
+    libdir = os.path.join(ROOT, "topopteval.jl_b200")
+    exe = tmp_path / "cantilever"
+    r = subprocess.run(["gcc", "-std=c99", "-O2", os.path.join(ROOT, "examples", "cantilever.c"), "-I" + os.path.join(ROOT, "include"),
+                        "-L" + libdir, "-ltopopt_b200", "-Wl,-rpath," + libdir, "-lm", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), "24", "8", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"(\d+) tets, (\d+) DOFs, nnz (\d+) .* deformation energy ([0-9.eE+-]+), compliance ([0-9.eE+-]+),", r.stdout)
+    assert m, r.stdout
+    assert int(m.group(2)) == int(g["24x8x4_ndofs"]) and int(m.group(3)) == int(g["24x8x4_nnz"])
+    e_ref, c_ref = float(g["24x8x4_energy"]), float(g["24x8x4_compliance"])
+    assert abs(float(m.group(4)) - e_ref) <= 1e-6 * e_ref and abs(float(m.group(5)) - c_ref) <= 1e-6 * c_ref
