@@ -1,6 +1,7 @@
 """CPU tests of the oracle itself: frozen golden values (tests/golden, generated from the reference's fixtures by
 tests/golden/make_golden.py), internal consistency of the restatement, and the reference's one analytic check."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -164,3 +165,23 @@ def test_boundary_selection_and_traction_known_answers(pkg, fo, hexm):
     assert abs(tot[2] - 160.0) < 1e-10 and abs(prob.f.sum() - 160.0) < 1e-10
     with pytest.raises(ValueError):
         fo.apply_uniform_surface_traction(prob, fo.get_boundary_facets(cells, []), [0.0, 0.0, -1.0])
+
+
+def test_tip_loaded_cantilever_energies_approach_beam_theory(golden_syn):
+    """Known-answer check of the frozen synthetic energies (oracle) and of the 1M / 10M anchors: a tip-loaded cantilever
+    (L = 60, b = 20, h = 4, E = 1, ν = 0.3, P = 1) stores ½Pδ with δ = PL³/(3EI) + PL/(κGA) = 675 + 2.3 (Timoshenko), i.e.
+    338.7.  Linear tets are too stiff, so the discrete energies rise monotonically towards that value from below as the mesh is
+    refined; the clamped wide section (b/h = 5, anticlastic curvature suppressed near the wall) keeps the limit a little under it."""
+    import json
+    P, L, b, h, E, nu = 1.0, 60.0, 20.0, 4.0, 1.0, 0.3
+    inertia = b * h ** 3 / 12.0
+    shear = P * L / ((5.0 / 6.0) * (E / (2 * (1 + nu))) * b * h)
+    e_beam = 0.5 * P * (P * L ** 3 / (3 * E * inertia) + shear)
+    assert abs(e_beam - 338.67) < 0.01
+    full = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_c3.json")))
+    seq = [float(golden_syn["12x4x2_energy"]), float(golden_syn["24x8x4_energy"]), full["C3_1M"]["energy"], full["C4_10M"]["energy"]]
+    assert all(a < b_ for a, b_ in zip(seq, seq[1:])), seq                    # stiffer than the continuum, less so with every refinement
+    assert seq[-1] < e_beam and 0.95 < seq[-2] / e_beam < seq[-1] / e_beam < 1.0, (seq, e_beam)
+    # first-order convergence in h for linear tets: the 1M → 10M step (h ratio 260/120) closes the gap to the limit by about that ratio
+    gap_1m, gap_10m = e_beam - seq[-2], e_beam - seq[-1]
+    assert 1.3 < gap_1m / gap_10m < 3.0, (gap_1m, gap_10m)
