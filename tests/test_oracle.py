@@ -185,3 +185,46 @@ def test_tip_loaded_cantilever_energies_approach_beam_theory(golden_syn):
     # first-order convergence in h for linear tets: the 1M → 10M step (h ratio 260/120) closes the gap to the limit by about that ratio
     gap_1m, gap_10m = e_beam - seq[-2], e_beam - seq[-1]
     assert 1.3 < gap_1m / gap_10m < 3.0, (gap_1m, gap_10m)
+
+
+@pytest.mark.parametrize("npc", [4, 8])
+def test_element_stiffness_known_answers(fo, npc):
+    """Independent facts about Kₑ that any correct restatement must satisfy (the reference's own tests pin none): symmetric, positive
+    semi-definite with EXACTLY six zero eigenvalues (rigid-body modes) on distorted cells, exact energy V·W(ε) for every linear
+    displacement field (both elements reproduce constant strain; degree-2 quadrature integrates it exactly), and for the unit cube
+    under uniaxial strain the closed form ½(λ+2μ)ε²V."""
+    rng = np.random.default_rng(11)
+    lam, mu = fo.create_material_model(3.0, 0.27)
+    if npc == 4:
+        X0 = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], float)
+    else:
+        X0 = np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)], float)
+    A = np.eye(3) + 0.2 * rng.standard_normal((3, 3))                      # affine map (keeps Hex8 faces planar) + a small warp for the hex
+    X = X0 @ A.T + (0.03 * rng.standard_normal(X0.shape) if npc == 8 else 0.0)
+    cells = np.arange(1, npc + 1, dtype=np.int64)[None, :]
+    ke = fo.element_stiffness(X, cells, lam, mu)[0]
+    assert np.max(np.abs(ke - ke.T)) <= 1e-13 * np.abs(ke).max()
+    w = np.linalg.eigvalsh(0.5 * (ke + ke.T))
+    assert np.sum(np.abs(w) <= 1e-12 * w.max()) == 6 and np.all(w >= -1e-12 * w.max()), w
+    # rigid-body modes explicitly
+    for k in range(3):
+        t = np.zeros((npc, 3)); t[:, k] = 1.0
+        wv = np.zeros(3); wv[k] = 1.0
+        r = np.cross(np.broadcast_to(wv, X.shape), X)
+        assert np.max(np.abs(ke @ t.reshape(-1))) <= 1e-12 * np.abs(ke).max()
+        assert np.max(np.abs(ke @ r.reshape(-1))) <= 1e-12 * np.abs(ke).max() * np.abs(r).max()
+    # constant-strain energy on the affine cell (no warp): ½uᵀKₑu = V·W(ε)
+    Xa = X0 @ A.T
+    kea = fo.element_stiffness(Xa, cells, lam, mu)[0]
+    vol = abs(np.linalg.det(A)) * (1.0 / 6.0 if npc == 4 else 1.0)
+    for _ in range(3):
+        G = 1e-3 * rng.standard_normal((3, 3))
+        u = (Xa @ G.T).reshape(-1)
+        eps = 0.5 * (G + G.T)
+        W = 0.5 * (lam * np.trace(eps) ** 2 + 2 * mu * np.sum(eps * eps))
+        assert abs(0.5 * u @ kea @ u - vol * W) <= 1e-12 * vol * W
+    # unit cell, uniaxial strain ε_xx = ε: energy ½(λ+2μ)ε²V
+    k0 = fo.element_stiffness(X0, cells, lam, mu)[0]
+    u = np.zeros((npc, 3)); u[:, 0] = 2e-3 * X0[:, 0]
+    v0 = 1.0 / 6.0 if npc == 4 else 1.0
+    assert abs(0.5 * u.reshape(-1) @ k0 @ u.reshape(-1) - 0.5 * (lam + 2 * mu) * (2e-3) ** 2 * v0) <= 1e-13 * v0
