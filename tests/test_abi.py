@@ -84,3 +84,31 @@ def test_header_is_plain_c_and_the_c_example_builds(tmp_path, have_gpu):
     if not have_gpu:
         r = subprocess.run([str(exe), "4", "2", "1"], capture_output=True, text=True)
         assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_struct_layouts_agree_across_c_python_julia(pkg):
+    """toe_pcg_stats / toe_timings cross the ABI by pointer: the field lists of the header, the ctypes mirror and the Julia shim
+    must be the same names and types in the same order."""
+    hdr = open(os.path.join(ROOT, "include", "topopt_b200.h")).read()
+    jl = open(os.path.join(ROOT, "topopteval.jl_b200", "julia", "TopOptEvalB200.jl")).read()
+    ctype = {"int64_t": "c_long", "int32_t": "c_int", "double": "c_double"}
+    jtype = {"int64_t": "Int64", "int32_t": "Int32", "double": "Float64"}
+
+    def c_fields(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for t, names in re.findall(r"\b(int64_t|int32_t|double)\s+([\w\s,]+?)\s*;", body):      # `double a, b, c;` declares three fields
+            out += [(t, n.strip()) for n in names.split(",")]
+        return out
+
+    for cname, pycls in (("toe_pcg_stats", pkg._lib.PcgStats), ("toe_timings", pkg._lib.Timings)):
+        cf = c_fields(cname)
+        assert len(cf) >= 9
+        assert [n for _, n in cf] == [n for n, _ in pycls._fields_], cname
+        assert [ctype[t] for t, _ in cf] == [t.__name__ for _, t in pycls._fields_], cname
+    # Julia: struct PcgStats ... end with `name::Type` entries
+    jbody = re.search(r"struct PcgStats\n(.*?)\nend", jl, re.S).group(1)
+    jf = re.findall(r"(\w+)::(\w+)", jbody)
+    cf = c_fields("toe_pcg_stats")
+    assert [(n, jtype[t]) for t, n in cf] == jf
