@@ -112,3 +112,41 @@ def test_struct_layouts_agree_across_c_python_julia(pkg):
     jf = re.findall(r"(\w+)::(\w+)", jbody)
     cf = c_fields("toe_pcg_stats")
     assert [(n, jtype[t]) for t, n in cf] == jf
+
+
+def test_julia_ccall_signatures_match_the_header():
+    """Julia is not installed here, so the shim cannot be run: every `ccall((:toe_x, LIB), ret, (types…), …)` in TopOptEvalB200.jl is
+    checked statically against the prototype of toe_x in include/topopt_b200.h — return type, number of arguments and the class of
+    each one (ctx, pointer-to-double / -int64 / -int, scalar int64 / double / int, struct pointer, byte string)."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "topopt_b200.h")).read(), flags=re.S)
+    jl = open(os.path.join(ROOT, "topopteval.jl_b200", "julia", "TopOptEvalB200.jl")).read()
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int|void|const char\*)\s+(toe_\w+)\s*\(([^;{]*?)\)\s*;", hdr, re.S):
+        protos[name] = (ret, [a.strip() for a in args.replace("\n", " ").split(",")] if args.strip() not in ("", "void") else [])
+
+    def cclass(a):
+        a = re.sub(r"\s+", " ", a)
+        for pat, cls in ((r"toe_ctx\s*\*\*", "ctx**"), (r"toe_ctx", "ctx*"), (r"toe_pcg_stats", "stats*"), (r"toe_timings", "timings*"),
+                         (r"double\s*\*|double \w+\[", "f64*"), (r"int64_t\s*\*", "i64*"), (r"int32_t\s*\*", "i32*"), (r"\bint\s*\*", "int*"),
+                         (r"char", "bytes"), (r"\bint64_t\b", "i64"), (r"\bdouble\b", "f64"), (r"\bint\b", "int")):
+            if re.search(pat, a):
+                return cls
+        raise AssertionError("unclassified C argument %r" % a)
+
+    jmap = {"Ptr{Cvoid}": "ctx*", "Ref{Ptr{Cvoid}}": "ctx**", "Ptr{Float64}": "f64*", "Ref{Float64}": "f64*", "Ptr{Int64}": "i64*", "Ref{Int64}": "i64*",
+            "Ptr{Int32}": "i32*", "Ref{Cint}": "int*", "Ptr{Cint}": "int*", "Int64": "i64", "Float64": "f64", "Cint": "int", "Ref{PcgStats}": "stats*",
+            "Ptr{UInt8}": "bytes", "Cstring": "bytes"}
+    rmap = {"int": "Cint", "void": "Cvoid", "const char*": "Cstring"}
+    calls = re.findall(r"ccall\(\(:(toe_\w+), LIB\),\s*(\w+),\s*\(([^)]*)\)", jl)
+    assert len(calls) >= 40
+    for name, ret, types in calls:
+        assert name in protos, "the shim calls %s, which the header does not declare" % name
+        cret, cargs = protos[name]
+        got = [jmap[t.strip()] for t in types.split(",") if t.strip()]
+        assert ret == rmap[cret] and got == [cclass(a) for a in cargs], (name, got, [cclass(a) for a in cargs])
+    # the path's entry points are all bound
+    used = {c[0] for c in calls}
+    for need in ("toe_create", "toe_destroy", "toe_set_mesh", "toe_build_dofs", "toe_build_pattern", "toe_assemble_lame", "toe_assemble_simp",
+                 "toe_add_nodal_force", "toe_add_volume_force", "toe_apply_dirichlet", "toe_solve_pcg", "toe_get_solution", "toe_energy", "toe_stresses",
+                 "toe_calculate_stresses", "toe_calculate_stresses_simp", "toe_comm_init", "toe_set_mesh_distributed"):
+        assert need in used, need

@@ -25,7 +25,7 @@ export setup_problem, create_material_model, create_simp_material_model,
        apply_fixed_boundary!, apply_sliding_boundary!, apply_force!,
        apply_volume_force!, apply_gravity!, apply_acceleration!, apply_variable_density_volume_force!,
        solve_system, solve_system_simp, solve_system_robust, solve_system_robust_simp, solve_system_adaptive,
-       calculate_stresses, calculate_stresses_simp, ferrite_dofhandler,
+       calculate_stresses, calculate_stresses_simp, ferrite_dofhandler, comm_unique_id,
        SolverConfig, element_energies, compliance,
        select_nodes_by_plane, select_nodes_by_circle, get_node_dofs, get_boundary_facets, compute_boundary_area,
        apply_surface_traction!, apply_uniform_surface_traction!
@@ -111,7 +111,17 @@ end
 create_simp_material_model(E0::Float64, nu::Float64, Emin::Float64 = 1e-6, p::Float64 = 1.0) = SimpModel(E0, nu, Emin, p)
 
 # ---- setup_problem (:151-185) ------------------------------------------------------------------------------------------
-function setup_problem(grid::Grid, interpolation_order::Int = 1; device::Integer = 0)
+"128-byte NCCL unique id: call on ONE process (rank 0) and hand the bytes to the others (MPI.Bcast!, Distributed.remotecall, a file …)."
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    st = ccall((:toe_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)
+    st == 0 || error(unsafe_string(ccall((:toe_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    return id
+end
+
+# `comm = (nranks, rank, id)`: one Julia process per GPU, every process passes the SAME global grid; the library partitions it,
+# and every later call is collective and takes / returns global data (INTEGRATION.md §5).  Default: a single GPU.
+function setup_problem(grid::Grid, interpolation_order::Int = 1; device::Integer = 0, comm = nothing)
     interpolation_order == 1 || error("only linear Lagrange interpolation is on the GPU path")
     cell_type = typeof(getcells(grid, 1))                                   # :157
     npc = cell_type <: Ferrite.Hexahedron ? 8 : 4
@@ -123,7 +133,15 @@ function setup_problem(grid::Grid, interpolation_order::Int = 1; device::Integer
     for (e, c) in enumerate(grid.cells); conn[:, e] .= c.nodes; end
     ctx = Ctx(device)
     GC.@preserve xyz conn begin
-        check(ctx, ccall((:toe_set_mesh, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Cint, Ptr{Int64}), ctx.ptr, nn, xyz, ne, npc, conn))
+        if comm === nothing
+            check(ctx, ccall((:toe_set_mesh, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Cint, Ptr{Int64}), ctx.ptr, nn, xyz, ne, npc, conn))
+        else
+            nranks, rank, id = comm
+            length(id) == 128 || error("comm id must be the 128 bytes of comm_unique_id()")
+            idb = convert(Vector{UInt8}, id)
+            check(ctx, ccall((:toe_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.ptr, nranks, rank, idb))
+            check(ctx, ccall((:toe_set_mesh_distributed, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Int64, Cint, Ptr{Int64}), ctx.ptr, nn, xyz, ne, npc, conn))
+        end
     end
     nd = Ref{Int64}(0); nnz = Ref{Int64}(0)
     check(ctx, ccall((:toe_build_dofs, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}), ctx.ptr, nd))
