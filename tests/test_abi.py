@@ -150,3 +150,37 @@ def test_julia_ccall_signatures_match_the_header():
                  "toe_add_nodal_force", "toe_add_volume_force", "toe_apply_dirichlet", "toe_solve_pcg", "toe_get_solution", "toe_energy", "toe_stresses",
                  "toe_calculate_stresses", "toe_calculate_stresses_simp", "toe_comm_init", "toe_set_mesh_distributed"):
         assert need in used, need
+
+
+def test_shims_cover_the_reference_export_list():
+    """every name FiniteElementAnalysis exports (FiniteElementAnalysis.jl:11-24, :70-87 — frozen here, the reference tree does not travel)
+    is defined by the Julia shim and by the Python mirror; `get_face_nodes` dispatches on Ferrite cell types and stays the reference's
+    own in Julia."""
+    exports = ["create_material_model", "setup_problem", "assemble_stiffness_matrix!", "get_node_dofs", "apply_fixed_boundary!", "apply_sliding_boundary!",
+               "apply_force!", "solve_system", "calculate_stresses", "create_simp_material_model", "assemble_stiffness_matrix_simp!",
+               "calculate_stresses_simp", "solve_system_simp", "solve_system_adaptive", "get_face_nodes", "select_nodes_by_plane", "select_nodes_by_circle",
+               "apply_volume_force!", "apply_gravity!", "apply_acceleration!", "apply_variable_density_volume_force!", "solve_system_robust",
+               "solve_system_robust_simp", "SolverConfig", "get_boundary_facets", "apply_surface_traction!", "apply_uniform_surface_traction!",
+               "compute_boundary_area"]
+    jl = open(os.path.join(ROOT, "topopteval.jl_b200", "julia", "TopOptEvalB200.jl")).read()
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    for name in exports:
+        assert hasattr(pkg, name.rstrip("!")), "Python mirror lacks %s" % name
+        if name == "get_face_nodes":
+            continue
+        pat = r"(?m)^(?:function\s+|Base\.@kwdef\s+struct\s+|struct\s+)?%s(?=[\s(])" % re.escape(name)
+        assert re.search(pat, jl), "Julia shim lacks %s" % name
+        assert re.search(r"export[^#]*?[\s,]%s(?=[\s,])" % re.escape(name), jl, re.S), "Julia shim does not export %s" % name
+    if os.path.exists("/root/reference/src/FiniteElementAnalysis/FiniteElementAnalysis.jl"):      # build container only: the frozen list is complete
+        ref = open("/root/reference/src/FiniteElementAnalysis/FiniteElementAnalysis.jl").read()
+        found, lines = set(), ref.splitlines()
+        for i, ln in enumerate(lines):
+            if not ln.startswith("export "):
+                continue
+            blk, j = ln[len("export "):], i
+            while blk.rstrip().endswith(","):                       # the list continues on the next line
+                j += 1
+                blk += lines[j]
+            found |= set(re.findall(r"[A-Za-z_]\w*!?", blk))
+        assert found == set(exports), (found - set(exports), set(exports) - found)
