@@ -184,3 +184,39 @@ def test_shims_cover_the_reference_export_list():
                 blk += lines[j]
             found |= set(re.findall(r"[A-Za-z_]\w*!?", blk))
         assert found == set(exports), (found - set(exports), set(exports) - found)
+
+
+def test_julia_ccalls_pass_as_many_arguments_as_they_declare():
+    """second static check of the shim: in every ccall the number of values after the type tuple equals the length of the tuple
+    (balanced-bracket parse), and brackets balance over the whole file"""
+    jl = open(os.path.join(ROOT, "topopteval.jl_b200", "julia", "TopOptEvalB200.jl")).read()
+
+    def split_top(s):
+        out, depth, cur = [], 0, ""
+        for ch in s:
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if ch == "," and depth == 0:
+                out.append(cur.strip()); cur = ""
+            else:
+                cur += ch
+        return out + ([cur.strip()] if cur.strip() else [])
+
+    n = 0
+    for m in re.finditer(r"ccall\(", jl):
+        i = j = m.end()
+        depth = 1
+        while depth:
+            depth += jl[j] in "([{"
+            depth -= jl[j] in ")]}"
+            j += 1
+        parts = split_top(jl[i:j - 1])
+        types = parts[2]
+        assert types.startswith("(") and types.endswith(")"), parts[0]
+        assert len([t for t in split_top(types[1:-1]) if t]) == len(parts) - 3, parts[0]
+        n += 1
+    assert n >= 40
+    code = re.sub(r'"(?:\\.|[^"\\])*"', '""', re.sub(r'"""(.*?)"""', '""', jl, flags=re.S))
+    code = re.sub(r"#.*", "", code)
+    for a, b in ("()", "[]", "{}"):
+        assert code.count(a) == code.count(b), (a, code.count(a), code.count(b))
