@@ -17,7 +17,8 @@ EMU_DIR = os.path.join(ROOT, "tests", "cuda_emu")
 # TOE_EMU_ASAN=1: AddressSanitizer build in its own object directory; run the tests with
 #   LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 TOE_EMU_ASAN=1 python -m pytest tests/test_emu_*.py
 ASAN = os.environ.get("TOE_EMU_ASAN") == "1"
-OBJDIR = "_asan" if ASAN else "_build"
+UBSAN = os.environ.get("TOE_EMU_UBSAN") == "1"      # -fsanitize=undefined (no preload needed): TOE_EMU_UBSAN=1 python -m pytest tests/test_emu_*.py
+OBJDIR = "_asan" if ASAN else ("_ubsan" if UBSAN else "_build")
 EMU_LIB = os.path.join(EMU_DIR, OBJDIR, "libtopopt_emu.so")
 
 
@@ -25,7 +26,10 @@ def build_emu(extra: str = "", opt: str = "-O2") -> str:
     if ASAN:
         extra = (extra + " -fsanitize=address -fno-omit-frame-pointer").strip()
         opt = "-O1"
-    cxx = ["CXX=/usr/bin/g++"] if ASAN and os.path.exists("/usr/bin/g++") else []      # the distribution's g++ ships libasan
+    elif UBSAN:
+        extra = (extra + " -fsanitize=undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer").strip()
+        opt = "-O1"
+    cxx = ["CXX=/usr/bin/g++"] if (ASAN or UBSAN) and os.path.exists("/usr/bin/g++") else []      # the distribution's g++ ships libasan
     env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}                    # the sanitizer runtime is for the tests, not for make / g++
     res = subprocess.run(["make", "-C", EMU_DIR, "-j8", "OPT=" + opt, "OBJDIR=" + OBJDIR] + cxx + (["EXTRA=" + extra] if extra else []),
                          capture_output=True, text=True, env=env)
