@@ -143,6 +143,34 @@ def run_reference(args, pkg):
     print(json.dumps(line), flush=True)
 
 
+def run_guarded(fn, timeout_s, on_failure):
+    """Runs the optional `fn()` with a deadline.  Returns None if there is nothing to run, True if it finished, False if it raised —
+    in which case `on_failure(reason)` has been called.  If `fn` is still running after `timeout_s` (a collective that never returns
+    cannot be cancelled), a watchdog thread calls `on_failure` and ends the PROCESS with exit code 0: the caller's results are out,
+    there is nothing left worth a hang."""
+    if fn is None:
+        return None
+    finished = threading.Event()
+
+    def watchdog():
+        if not finished.wait(timeout_s):
+            try:
+                on_failure("timed out after %.0f s" % timeout_s)
+            finally:
+                sys.stdout.flush()
+                os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    try:
+        fn()
+    except BaseException as ex:  # noqa: BLE001 — an optional extra must never cost the headline line
+        finished.set()
+        on_failure("%s: %s" % (type(ex).__name__, str(ex)[:300]))
+        return False
+    finished.set()
+    return True
+
+
 # ------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------
@@ -320,17 +348,19 @@ def run_b200(args, pkg):
 
     h2d = pts.nbytes + cells.nbytes + load.nbytes + pres.nbytes
     d2h = u.nbytes + 2 * 8 + 128
+    info = {"ndofs": ctx.ndofs, "nnz": ctx.nnz, "transport": ctx.comm_info()["transport"]}      # read now: the probes below re-set-up the ctx
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: structured-tet cantilever %dx%dx%d cubes x 6 = %d Tet4, %d DOFs, nnz %d; E=1, nu=0.3, solid densities, clamp x=0, "
-                                   "tip load -1 z; Jacobi-PCG atol=rtol=1e-8 (Krylov.jl M-norm)" % ((args.workload,) + dims + (ne_total, ctx.ndofs, ctx.nnz)),
+                                   "tip load -1 z; Jacobi-PCG atol=rtol=1e-8 (Krylov.jl M-norm)" % ((args.workload,) + dims + (ne_total, info["ndofs"], info["nnz"])),
                        "operator": "matrix-free EbE" if mf else "assembled block-CSR", "parallelism": "dd%d" % world,
-                       "exchange": ctx.comm_info()["transport"],
-                       "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (ctx.nnz * 8 / 1e9),
+                       "exchange": info["transport"],
+                       "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (info["nnz"] * 8 / 1e9),
                        "wall_ms_per_step": 1e3 * wall_s / args.steps, "measurement_attempts": attempts},
             "clocks": clocks,
             "e2e": {"value": None if e2e_invalid else ne_total * e2e_steps / e2e_s, "invalid": e2e_invalid, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -355,7 +385,54 @@ def run_b200(args, pkg):
                                     "sample": "%dx%dx%d-cube cantilever = %d tets, full path in %.1f s (assemble %.0f el/s, PCG %d it); C restatement of the "
                                               "reference's loops, single core like the reference (no threading in TopOptEval.jl); not Julia"
                                               % (CPU_SAMPLE + (cb["ne"], cb["seconds"], cb["assemble_elements_per_s"], cb["niter"]))}
-        print(json.dumps(line), flush=True)
+
+    # ---- N > 1 extra, never part of `value`: the opt-in exchange transports on the same partitioned workload ----------------------------
+    # Everything the line needs is measured by now.  The probes re-set-up the ctx with another transport (first time on real NCCL /
+    # NVLink for the all-gather one), so they run under a watchdog: whatever happens in there — an exception, a collective that never
+    # returns — rank 0 still prints the line (with what the probes delivered so far) and every rank leaves.
+    emit_lock, emitted = threading.Lock(), []
+
+    def emit(extra):
+        with emit_lock:                                              # exactly ONE line, whoever gets here first (main thread or watchdog)
+            if emitted:
+                return
+            emitted.append(True)
+            if line is not None:
+                line["stages"]["exchange_transports"] = extra
+                print(json.dumps(line), flush=True)
+
+    probes = {}
+
+    def transport_probes():
+        for name, env in (("nccl-allgather", {"TOE_DIST_XCHG": "allgather"}), ("peer-memory", {"TOE_DIST_P2P": "1"})):
+            if name == info["transport"]:
+                continue
+            os.environ.update(env)
+            try:
+                setup()
+                got = ctx.comm_info()["transport"]
+                stw, _, _ = step()                                   # first solve after a set-up: warm-up
+                barrier()
+                ctx.timer_start()
+                stp, ep, _ = step()
+                dev = ctx.timer_stop()
+                barrier()
+                probes[name] = {"transport": got, "ms_per_step": 1e3 * max_over_ranks(dev), "pcg_seconds": ctx.timings()["solve"],
+                                "pcg_iterations": int(stp["niter"]), "converged": bool(stp["converged"]),
+                                "restarts": int(stw.get("restarts", 0)) + int(stp.get("restarts", 0)), "energy": ep,
+                                "energy_rel_diff_vs_default": abs(ep - e) / abs(e)}
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+
+    clean = run_guarded(transport_probes if (world > 1 and not getattr(args, "no_transport_probes", False)) else None, 150.0,
+                        lambda why: emit(dict(probes, error=why)))
+    if clean is None:
+        emit(None)                                                   # nothing to probe (single GPU or switched off)
+    elif clean:
+        emit(dict(probes, note="opt-in transports, one timed step each after a fresh set-up + warm-up step; never in `value`"))
+    else:
+        os._exit(0)                                                  # a probe failed: the line is out (emit ran), the ctx may be unusable — leave without teardown
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -442,6 +519,7 @@ def main():
     ap.add_argument("--matrix-free", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-two-level", action="store_true", help="skip the extra two-level-preconditioner solve reported in stages")
+    ap.add_argument("--no-transport-probes", action="store_true", help="N > 1: skip the opt-in exchange transports reported in stages.exchange_transports")
     ap.add_argument("--no-variants", action="store_true", help="skip the opt-in kernel variants (child processes) reported in stages.variants")
     args = ap.parse_args()
     import __graft_entry__ as graft

@@ -75,3 +75,43 @@ def test_variants_probe_sections_on_emulated_build(monkeypatch, capsys, section,
         assert out[key]["rows"]["max_rel_diff_Kx_vs_gather"] < 1e-13 and out[key]["rows"]["ms_min"] > 0
     else:
         assert out[key]["pipe"]["bit_identical_to_tile"] is True and out[key]["pipe"]["ms"] > 0
+
+
+def test_bench_partitioned_flow_on_emulated_build(monkeypatch):
+    """The N > 1 control flow of bench.py (re-measurement loop, e2e arm with restarts, the guarded transport probes) cannot meet real
+    NCCL here; it is driven with WORLD_SIZE=2 against ONE emulated rank (a 1-rank communicator, torch.distributed stubbed) so that
+    every statement of that path executes at least once: the line must come out once, complete, with the probes' entries."""
+    import torch
+    import torch.distributed as tdist
+    pkg, lib = emu_support.load_emu()
+    import bench
+    monkeypatch.setenv("WORLD_SIZE", "2"); monkeypatch.setenv("RANK", "0"); monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{kk: vv for kk, vv in k.items() if kk != "device"}))
+    for name in ("init_process_group", "barrier", "all_reduce", "destroy_process_group"):
+        monkeypatch.setattr(tdist, name, lambda *a, **k: None)
+
+    def one_rank_context(dist, local_rank):
+        ctx = pkg.Context(local_rank)
+        ctx.comm_init(1, 0, pkg.Context.comm_unique_id())
+        return ctx
+    monkeypatch.setattr(pkg.parallel, "create_distributed_context", one_rank_context)
+    args = types.SimpleNamespace(gpus=2, steps=1, warmup=1, impl="b200", workload="toy", matrix_free=False, no_cpu_baseline=True, no_two_level=True,
+                                 no_variants=True, no_transport_probes=False)
+    buf = io.StringIO()
+    with emu_support.emulated(pkg, lib), redirect_stdout(buf):
+        bench.run_b200(args, pkg)
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["config"]["parallelism"] == "dd2" and d["config"]["measurement_attempts"] == 1
+    assert d["e2e"]["invalid"] is None and d["e2e"]["pcg_restarts"] == 0 and d["stages"]["pcg_restarts"] == 0
+    assert "cpu_baseline" not in d and d["stages"]["local_sizes"] is not None
+    xt = d["stages"]["exchange_transports"]
+    assert "error" not in xt and set(xt) == {"nccl-allgather", "peer-memory", "note"}
+    for name in ("nccl-allgather", "peer-memory"):
+        assert xt[name]["converged"] and xt[name]["pcg_iterations"] == d["stages"]["pcg_iterations"] and xt[name]["energy_rel_diff_vs_default"] < 1e-12

@@ -121,3 +121,25 @@ def test_export_boundary_conditions(pkg, tmp_path, hexm):
     # no marked face at all: an empty (but valid) file, like the reference
     out2 = pkg.export_boundary_conditions(grid, None, set(), set(), str(tmp_path / "bc_empty"))
     assert os.path.getsize(out2) > 0
+
+
+def test_bench_run_guarded(tmp_path):
+    """bench.py's wrapper around optional extras: nothing to run → None; finishes → True; raises → False after reporting; still running
+    at the deadline → the watchdog reports and ends the process with exit code 0 (checked in a child process)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    seen = []
+    assert bench.run_guarded(None, 1.0, seen.append) is None and seen == []
+    assert bench.run_guarded(lambda: None, 5.0, seen.append) is True and seen == []
+
+    def boom():
+        raise RuntimeError("probe failed")
+    assert bench.run_guarded(boom, 5.0, seen.append) is False and len(seen) == 1 and "RuntimeError: probe failed" in seen[0]
+    code = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+            "bench.run_guarded(lambda: time.sleep(60), 0.5, lambda why: print('LINE', why, flush=True))\n"
+            "print('NOT REACHED')\n" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "LINE timed out after" in r.stdout and "NOT REACHED" not in r.stdout, r.stdout + r.stderr
