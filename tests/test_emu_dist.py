@@ -106,7 +106,7 @@ def test_partitioned_equals_single_ctx(emu, world, dims, simp, mf):
     y_single = single.spmv(x, matrix_free=mf)
     single.close()
     assert ref["conv"] == 1
-    ranks = _run_ranks(pkg, world, prob, mf, repeats=2)
+    ranks = _run_ranks(pkg, world, prob, mf, repeats=2 if world <= 4 else 1)      # re-set-up reproducibility at N = 2 and 4
     r0 = ranks[0][-1]
     counts = np.bincount(r0["part"], minlength=world)
     assert counts.max() - counts.min() <= 1, counts
@@ -172,7 +172,7 @@ def test_allgather_exchange_transport(emu, world, dims, simp, mf, monkeypatch):
         assert np.array_equal(ag[rk][-1]["spmv"], ref[rk][-1]["spmv"])
 
 
-@pytest.mark.parametrize("world,dims,simp,mf", [(4, (16, 4, 2), True, False), (2, (10, 4, 3), False, True)])
+@pytest.mark.parametrize("world,dims,simp,mf", [(4, (12, 4, 2), True, False), (2, (8, 4, 2), False, True)])
 def test_two_level_preconditioner_on_partitions(emu, world, dims, simp, mf, monkeypatch):
     """Jacobi + rigid-body coarse space on a partitioned ctx: per-box sums over OWNED nodes + allreduce, coarse operator probed
     through the interface-summed operator; must reproduce the single-ctx two-level solve (same boxes, same iteration count ±1)."""
