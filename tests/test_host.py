@@ -143,3 +143,42 @@ def test_bench_run_guarded(tmp_path):
             "print('NOT REACHED')\n" % root)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "LINE timed out after" in r.stdout and "NOT REACHED" not in r.stdout, r.stdout + r.stderr
+
+
+def _ascii_vtu(path, points, cells, types, density):
+    conn = " ".join(str(n) for c in cells for n in c)
+    offs = " ".join(str(o) for o in np.cumsum([len(c) for c in cells]))
+    xml = ('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="1.0" byte_order="LittleEndian">\n<UnstructuredGrid>\n'
+           '<Piece NumberOfPoints="%d" NumberOfCells="%d">\n<Points>\n<DataArray type="Float64" NumberOfComponents="3" format="ascii">\n%s\n</DataArray>\n</Points>\n'
+           '<Cells>\n<DataArray type="Int64" Name="connectivity" format="ascii">\n%s\n</DataArray>\n<DataArray type="Int64" Name="offsets" format="ascii">\n%s\n</DataArray>\n'
+           '<DataArray type="UInt8" Name="types" format="ascii">\n%s\n</DataArray>\n</Cells>\n'
+           '<CellData>\n<DataArray type="Float64" Name="density" format="ascii">\n%s\n</DataArray>\n</CellData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n'
+           % (len(points), len(cells), " ".join("%r" % float(v) for v in np.asarray(points).reshape(-1)), conn, offs, " ".join(map(str, types)),
+              " ".join("%r" % float(v) for v in density)))
+    open(path, "w").write(xml)
+
+
+def test_import_mesh_ragged_cell_types(pkg, tmp_path):
+    """A .vtu with mixed cell types (ragged connectivity): like MeshImport.jl:97-125 the dominant volume type wins, the other cells and
+    their cell data are dropped, ids become 1-based; ASCII DataArrays (no appended block) are read as well."""
+    pts = np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1), (2, 0, 0), (2, 1, 0), (2, 0, 1), (2, 1, 1)], float)
+    hex0 = [0, 1, 2, 3, 4, 5, 6, 7]
+    hex1 = [1, 8, 9, 2, 5, 10, 11, 6]
+    tets = [[0, 1, 3, 4], [1, 2, 3, 6], [1, 5, 4, 6]]
+    # three tets + one hex: tets win
+    p = str(tmp_path / "mixed_tet.vtu")
+    _ascii_vtu(p, pts, tets + [hex1], [10, 10, 10, 12], [0.1, 0.2, 0.3, 0.9])
+    g = pkg.import_mesh(p)
+    assert g.cell_type == 10 and np.array_equal(g.cells, np.array(tets) + 1)
+    assert np.array_equal(pkg.extract_cell_density(p), [0.1, 0.2, 0.3])
+    # two hexes + one tet (tet listed first): hexes win, order of the kept cells preserved
+    p = str(tmp_path / "mixed_hex.vtu")
+    _ascii_vtu(p, pts, [tets[0], hex0, hex1], [10, 12, 12], [0.5, 0.6, 0.7])
+    g = pkg.import_mesh(p)
+    assert g.cell_type == 12 and np.array_equal(g.cells, np.array([hex0, hex1]) + 1) and g.getncells() == 2
+    assert np.array_equal(pkg.extract_cell_density(p), [0.6, 0.7])
+    # surface-only file (triangles): not a volume mesh
+    p = str(tmp_path / "tri.vtu")
+    _ascii_vtu(p, pts, [[0, 1, 2], [0, 2, 3]], [5, 5], [1.0, 1.0])
+    with pytest.raises((ValueError, pkg.TopOptError)):
+        pkg.import_mesh(p)
