@@ -167,3 +167,26 @@ def test_results_do_not_depend_on_block_order(emu):
                 assert same, "block order %d changes %s" % (mode, k)
     finally:
         lib.emu_set_block_order(0)
+
+
+def test_maximum_sizes_are_refused_before_anything_is_read(emu):
+    """device indices are 32-bit: meshes beyond that (nn > (2^31-1)/3 nodes, ne·npc > 2^31-1 connectivity entries, more cells than the
+    packed (cell, a, b) contribution lists hold) must come back as an error — checked with the size arguments alone, before the
+    library touches the (tiny) arrays behind the pointers — and leave the ctx usable"""
+    import ctypes as C
+    pkg, lib = emu
+    ctx = pkg.Context(0)
+    pts, cells = pkg.meshgen.cantilever(2, 1, 1)
+    xyz = np.ascontiguousarray(pts, dtype=np.float64); conn = np.ascontiguousarray(cells, dtype=np.int64)
+    dp = xyz.ctypes.data_as(C.POINTER(C.c_double)); ip = conn.ctypes.data_as(C.POINTER(C.c_int64))
+    for nn, ne, npc in ((2 ** 31, 1, 4), ((2 ** 31 - 1) // 3 + 1, 1, 4), (8, 2 ** 29, 4), (8, 2 ** 28, 8), (0, 1, 4), (8, 0, 4), (8, 1, 5)):
+        st = lib.toe_set_mesh(ctx.h, nn, dp, ne, npc, ip)
+        assert st < 0, (nn, ne, npc)
+        msg = lib.toe_last_error(ctx.h).decode()
+        assert ("too large" in msg) or ("empty mesh" in msg) or ("unsupported cell type" in msg), msg
+    st = lib.toe_set_mesh_distributed(ctx.h, 2 ** 31, dp, 1, 4, ip)
+    assert st < 0                                                   # no communicator, and too large anyway
+    ctx.set_mesh(pts, cells); ctx.build_dofs(); ctx.build_pattern()       # the ctx survived all of it
+    ctx.assemble_lame(0.5, 0.4)
+    assert np.all(ctx.diagonal() > 0)
+    ctx.close()
