@@ -82,7 +82,7 @@ def test_boundary_selection_and_surface_traction(pkg, fo, golden_c1):
 
 def test_two_level_preconditioner(ctx, pkg, fo):
     import two_level_checks as tc
-    tc.check_two_level(pkg, fo, ctx, [((8, 3, 2), False, (4, 2, 1), False), ((5, 2, 2), False, (3, 2, 2), True), ((5, 3, 2), True, (3, 1, 1), False)], auto_dims=(12, 4, 2), light_after_first=True)
+    tc.check_two_level(pkg, fo, ctx, [((6, 3, 2), False, (4, 2, 1), False), ((5, 2, 2), False, (3, 2, 2), True), ((5, 3, 2), True, (3, 1, 1), False)], auto_dims=(12, 4, 2), light_after_first=True)
 
 
 def test_c_example_against_the_oracle(emu, fo, tmp_path):

@@ -57,9 +57,9 @@ def test_no_device_allocation_survives_destroy(emu):
     pkg, lib = emu
     base = lib.emu_live_allocations()
     ctx = pkg.Context(0)
-    _full_pass(pkg, ctx, (8, 3, 2), False)
-    _full_pass(pkg, ctx, (9, 3, 3), False, two_level=False)   # larger mesh on the same ctx: buffers grow
-    _full_pass(pkg, ctx, (4, 2, 2), True, two_level=False)     # Hex8, smaller: buffers are reused
+    _full_pass(pkg, ctx, (6, 2, 2), False)
+    _full_pass(pkg, ctx, (8, 3, 2), False, two_level=False)   # larger mesh on the same ctx: buffers grow
+    _full_pass(pkg, ctx, (3, 2, 2), True, two_level=False)     # Hex8, smaller: buffers are reused
     assert lib.emu_live_allocations() > base
     assert lib.emu_check_all_guards() == 0, "a device allocation was written out of bounds"
     ctx.close()
