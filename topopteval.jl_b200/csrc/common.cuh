@@ -172,8 +172,13 @@ inline int toe_fail(toe_ctx* c, int code, const char* fmt, ...) {
 #define TRY(call) do { int _s = (call); if (_s != TOE_OK) return _s; } while (0)
 
 #ifndef TOE_EMU
+// a launch that the runtime refuses (bad configuration, shared-memory opt-in missing, sticky error) fails HERE, by kernel name, not
+// at some later synchronisation; cudaPeekAtLastError is a host-side read (also legal during stream capture)
 #define LAUNCH(ctx, kern, grid, block, smem, ...) do { \
-    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; \
+    cudaError_t _le = cudaPeekAtLastError(); \
+    if (_le != cudaSuccess) return toe_fail((ctx), TOE_ERR_CUDA, "launch of %s <<<%u, %u, %zu B>>> failed: %s (%s)", #kern, (unsigned)(grid), (unsigned)(block), \
+                                            (size_t)(smem), cudaGetErrorName(_le), cudaGetErrorString(_le)); } while (0)
 // dynamic shared memory of the running block
 #define TOE_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
 typedef unsigned smem_ptr_t;       // 32-bit shared-window address, as the mbarrier / bulk-copy PTX wants it
