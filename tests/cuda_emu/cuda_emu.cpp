@@ -456,6 +456,7 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
     return cudaSuccess;
 }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+cudaError_t cudaPeekAtLastError(void) { return rank_state().last_error; }
 cudaError_t cudaGetLastError(void) { Rank& r = rank_state(); cudaError_t e = r.last_error; r.last_error = cudaSuccess; return e; }
 const char* cudaGetErrorName(cudaError_t e) {
     switch (e) { case 0: return "cudaSuccess"; case 1: return "cudaErrorInvalidValue"; case 2: return "cudaErrorMemoryAllocation";

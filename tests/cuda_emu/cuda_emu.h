@@ -83,6 +83,7 @@ cudaError_t cudaEventSynchronize(cudaEvent_t e);
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaGetLastError(void);
+cudaError_t cudaPeekAtLastError(void);
 const char* cudaGetErrorName(cudaError_t e);
 const char* cudaGetErrorString(cudaError_t e);
 cudaError_t cudaSetDevice(int d);

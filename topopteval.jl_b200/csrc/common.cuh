@@ -188,7 +188,10 @@ typedef unsigned smem_ptr_t;       // 32-bit shared-window address, as the mbarr
     auto _args = std::make_tuple(__VA_ARGS__); \
     emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [_args]() { std::apply([](auto... a) { kern(a...); }, _args); }, \
                 reinterpret_cast<const void*>(&kern)); \
-    (ctx)->launches++; } while (0)
+    (ctx)->launches++; \
+    cudaError_t _le = cudaPeekAtLastError(); \
+    if (_le != cudaSuccess) return toe_fail((ctx), TOE_ERR_CUDA, "launch of %s <<<%u, %u, %zu B>>> failed: %s (%s)", #kern, (unsigned)(grid), (unsigned)(block), \
+                                            (size_t)(smem), cudaGetErrorName(_le), cudaGetErrorString(_le)); } while (0)
 #define TOE_DYN_SMEM(type, name, align) type* name = reinterpret_cast<type*>(emu::dyn_smem())
 typedef size_t smem_ptr_t;
 #endif
