@@ -167,8 +167,9 @@ inline int toe_fail(toe_ctx* c, int code, const char* fmt, ...) {
     return code;
 }
 
-#define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) \
-    return toe_fail(ctx, TOE_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); } while (0)
+// a reported error is also cleared from the runtime's last-error slot (sticky ones stay), so that it is not blamed on the next launch
+#define CU(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cudaGetLastError(); \
+    return toe_fail(ctx, TOE_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); } } while (0)
 #define TRY(call) do { int _s = (call); if (_s != TOE_OK) return _s; } while (0)
 
 #ifndef TOE_EMU
