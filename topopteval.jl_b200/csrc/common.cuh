@@ -175,7 +175,9 @@ inline int toe_fail(toe_ctx* c, int code, const char* fmt, ...) {
 #ifndef TOE_EMU
 // a launch that the runtime refuses (bad configuration, shared-memory opt-in missing, sticky error) fails HERE, by kernel name, not
 // at some later synchronisation; cudaPeekAtLastError is a host-side read (also legal during stream capture)
+// (the slot is cleared first: a non-sticky error left behind by a library call — NCCL / IPC probing — has been handled by whoever made it)
 #define LAUNCH(ctx, kern, grid, block, smem, ...) do { \
+    (void)cudaGetLastError(); \
     kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; \
     cudaError_t _le = cudaPeekAtLastError(); \
     if (_le != cudaSuccess) return toe_fail((ctx), TOE_ERR_CUDA, "launch of %s <<<%u, %u, %zu B>>> failed: %s (%s)", #kern, (unsigned)(grid), (unsigned)(block), \
