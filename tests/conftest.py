@@ -17,6 +17,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """The GPU gate must be honest: no test of tests/test_gpu_*.py may carry an unconditional `skip` mark after collection (in round 1
+    a mark set on an imported function by the emulation suite silently skipped every solve-parity test on the B200).  Conditional
+    skips (`skipif` on the GPU count, pytest.skip() at run time) are not affected."""
+    leaked = [it.nodeid for it in items if os.path.basename(str(it.fspath)).startswith("test_gpu_") and it.get_closest_marker("skip") is not None]
+    if leaked:
+        raise pytest.UsageError("unconditional skip marks on GPU tests (leaked from another module?): %s" % leaked[:5])
+
+
 @pytest.fixture(scope="session")
 def pkg():
     return graft.load_package()

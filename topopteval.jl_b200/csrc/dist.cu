@@ -13,6 +13,7 @@
 #include <nccl.h>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 struct NcclApi {
     void* h = nullptr;
@@ -459,7 +460,7 @@ __global__ void k_unpack_sum(const int* __restrict__ if_node, const int* __restr
 // of real solves; the restart logic in solve_pcg remains as the safety net.
 static int dist_warm_up(toe_ctx* ctx) {
     DistState* d = ctx->dist;
-    if (!d || d->nranks == 1 || d->warmed) return TOE_OK;
+    if (!d || d->nranks == 1 || d->warmed || !getenv("TOE_DIST_WARMUP")) return TOE_OK;      // opt-in (A/B diagnostic); off by default
     size_t n = 3 * (size_t)ctx->nq;
     DevBuf<double> scratch; CU(scratch.alloc(n + 2));
     CU(cudaMemsetAsync(scratch.p, 0, (n + 2) * sizeof(double), ctx->stream));

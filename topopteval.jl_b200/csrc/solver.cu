@@ -178,8 +178,11 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
                 y[row] = acc;
                 if (CG) dot += acc * xrow;
             }
+            // every thread orders its own generic-proxy accesses to the stage (slot products written, row sums read) before the
+            // async-proxy refill; only then does the group meet and release the stage
+            fence_proxy_async();
             consumer_sync(group);
-            if (gt == 0) { fence_proxy_async(); mbar_arrive(smem_u32(bars + SPMV_STAGES + st)); }   // stage may be refilled
+            if (gt == 0) mbar_arrive(smem_u32(bars + SPMV_STAGES + st));   // stage may be refilled
         }
     }
     if (CG) {
