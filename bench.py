@@ -4,13 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # B200 arm (libtopopt_b200.so through the C ABI)
     python bench.py --impl reference --steps K --warmup W    # CPU arm: C restatement of the reference path (oracle/)
 
-A *step* is one pass of the hot path over the synthetic structured-tet cantilever: assemble K (SIMP-capable Tet4
-kernel, solid densities) → tip load → Ferrite-style Dirichlet → Jacobi-PCG to 1e-8 (Krylov.jl criterion) → per-element
-strain energy + compliance.  `value` = elements through the whole step per second with mesh, DOF map and sparsity
-pattern already resident in HBM; `e2e` = the same metric through the host API with HOST buffers (H2D of the mesh, DOF
-numbering + pattern build, the step, D2H of u) — i.e. what a reference user's script does between `setup_problem` and
-`solve_system`.  N=1 workload: the 10M-tet beam the metric is quoted on (fits one B200); N>1: the same 10M-tet beam
-partitioned over N GPUs (strong scaling), NCCL halo exchange + allreduce.
+A *step* is one pass of the hot path over the synthetic structured-tet cantilever: assemble K (SIMP-capable Tet4 kernel, solid
+densities) → tip load → Ferrite-style Dirichlet → Jacobi-PCG to 1e-8 (Krylov.jl criterion) → per-element strain energy + compliance.
+BASELINE.json's metric has two halves — elements assembled/s and PCG seconds to 1e-8 on the 10M-tet beam — reported as
+`metric_parts`; `value` is the whole-job throughput that contains both: elements through one full step per second, with mesh, DOF
+map and sparsity pattern resident in HBM.  `e2e` = the same through the host API with HOST buffers (H2D of the mesh, DOF numbering +
+pattern build, the step, D2H of u).  N=1: the 10M-tet beam (fits one B200); N>1: the same beam partitioned over N GPUs (strong
+scaling), NCCL interface exchange + allreduce.
+
+No retries anywhere: a step that does not converge, an exception or the global deadline end the run with ONE JSON line that carries
+`"error"` and the stage reached, and a non-zero exit code.
 """
 from __future__ import annotations
 
@@ -27,12 +30,40 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+T_START = time.perf_counter()
 
 WORKLOADS = {"C3_1M": (120, 50, 28), "C4_10M": (260, 110, 58), "C5_60M": (480, 200, 104), "tiny": (24, 8, 4), "toy": (8, 3, 2), "200k": (96, 32, 12)}
-CPU_SAMPLE = tuple(int(x) for x in os.environ.get("TOE_BENCH_CPU_SAMPLE", "60,20,8").split(","))   # 57 600 tets: ≈8 s (here) / ≈3 s (GPU box) of single-core CPU work per step
 TOL = 1e-8
-ITMAX = 40000                     # 13 689 iterations are needed at 10M tets; a stagnating solve must end quickly, not after 100 000
-METRIC = "elements assembled+solved/s (assemble -> Jacobi-PCG to 1e-8 -> strain energy; 10M-tet beam)"
+ITMAX = 40000                     # 13 689 iterations are needed at 10M tets; a stagnating solve must end quickly
+METRIC = "elements assembled/s; PCG solve time to 1e-8 on 10M-tet beam at 1/2/4/8 B200"
+VALUE_DEF = ("value = elements through one full step (assemble + load + Dirichlet + Jacobi-PCG to 1e-8 + strain energy) per second; the two "
+             "halves of the metric are in metric_parts")
+# CPU arm: the C oracle cannot restate the whole 10M-tet step in bench time (≈2.3 h on one core), so it times a bounded sample and
+# extrapolates: assembly rate on a slice, PCG seconds per iteration on the 1M-tet problem scaled by nnz
+CPU_MESH = os.environ.get("TOE_BENCH_CPU_MESH", "C3_1M")
+CPU_SLICE = int(os.environ.get("TOE_BENCH_CPU_SLICE", "100000"))
+CPU_ITERS = int(os.environ.get("TOE_BENCH_CPU_ITERS", "20"))
+GOLDEN_FULLSIZE = os.path.join(ROOT, "tests", "golden", "fullsize_c3.json")
+
+
+def structured_counts(dims):
+    """nodes, cells, nnz of the 6-tet split of an nx×ny×nz box (closed form, tests/fullsize_properties.py)."""
+    nx, ny, nz = dims
+    nn = (nx + 1) * (ny + 1) * (nz + 1)
+    edges = (nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz
+             + nx * ny * (nz + 1) + nx * nz * (ny + 1) + ny * nz * (nx + 1) + nx * ny * nz)
+    return nn, 6 * nx * ny * nz, 9 * (nn + 2 * edges)
+
+
+def static_config(args):
+    """The same dict in both arms (the driver compares them)."""
+    dims = WORKLOADS[args.workload]
+    nn, ne, nnz = structured_counts(dims)
+    return {"workload": "%s: structured-tet cantilever %dx%dx%d cubes x 6 = %d Tet4, %d DOFs, nnz %d; E=1, nu=0.3, solid densities, clamp x=0, "
+                        "tip load -1 z; Jacobi-PCG atol=rtol=1e-8 (Krylov.jl M-norm)" % ((args.workload,) + dims + (ne, 3 * nn, nnz)),
+            "operator": "matrix-free EbE" if args.matrix_free else "assembled block-CSR", "parallelism": "dd%d" % args.gpus,
+            "tolerance": TOL, "value_definition": VALUE_DEF,
+            "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (nnz * 8 / 1e9)}
 
 
 def measured_peaks():
@@ -97,84 +128,162 @@ def make_problem(pkg, dims):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: C restatement of the reference path (single core — the reference has no threading)
+# progress / deadline: whatever happens, rank 0 prints exactly one JSON line
 # ------------------------------------------------------------------------------------------------------------
-def cpu_step(pkg, dims):
-    from oracle import c_oracle
-    pts, cells, fixed, load = make_problem(pkg, dims)
-    lam, mu = pkg.create_material_model(1.0, 0.3)
-    t0 = time.perf_counter()
-    cp = c_oracle.CProblem(pts, cells)                       # first-touch DOFs + sorted CSC pattern
-    cp.assemble(lam_mu=(lam, mu))                            # (q,i,j) loops + sorted-merge assembly
-    cp.apply_force(load, [0.0, 0.0, -1.0])
-    pres0 = (cp.node_first_dof[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1)
-    cp.apply_dirichlet(pres0)
-    u, niter, solved, _ = cp.pcg(TOL, ITMAX)
-    energy = cp.energy(u)
-    dt = time.perf_counter() - t0
-    return {"seconds": dt, "ne": cp.ne, "ndofs": cp.n, "niter": int(niter), "solved": solved, "energy": energy,
-            "stage_seconds": dict(cp.t), "assemble_elements_per_s": cp.ne / cp.t["assemble"]}
+class Progress:
+    def __init__(self, args, rank):
+        self.args, self.rank = args, rank
+        self.stage = "start"
+        self.verbose = os.environ.get("TOE_BENCH_VERBOSE") == "1"
+        self.lock = threading.Lock()
+        self.printed = False
+        self.partial = {}
+
+    def at(self, stage, *extra):
+        self.stage = stage
+        if self.verbose:
+            print("[rank %d +%.1fs] %s" % (self.rank, time.perf_counter() - T_START, stage), *extra, file=sys.stderr, flush=True)
+
+    def emit(self, line):
+        with self.lock:
+            if self.printed:
+                return
+            self.printed = True
+            if self.rank == 0 and line is not None:
+                print(json.dumps(line), flush=True)
+
+    def fail(self, why, code):
+        a = self.args
+        line = {"metric": METRIC, "value": None, "unit": "elements/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "error": why,
+                "stage": self.stage, "elapsed_s": time.perf_counter() - T_START, "config": static_config(a), "partial": self.partial}
+        if a.impl == "reference":
+            line["impl"] = "reference"
+        self.emit(line)
+        print("bench.py: %s (stage: %s)" % (why, self.stage), file=sys.stderr, flush=True)
+        sys.stdout.flush()
+        os._exit(code)           # no teardown: a communicator with a rank stuck in a collective cannot be destroyed
+
+    def watchdog(self, seconds):
+        def run():
+            time.sleep(max(1.0, seconds - (time.perf_counter() - T_START)))
+            if not self.printed:
+                self.fail("deadline of %.0f s reached" % seconds, 3)
+        threading.Thread(target=run, daemon=True).start()
 
 
-def run_reference(args, pkg):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: C restatement of the reference path (single core — the reference has no threading), bounded sample + extrapolation
+# ------------------------------------------------------------------------------------------------------------
+class CpuSample:
+    """Set-up once (untimed, like the B200 arm's resident mesh + pattern): the 1M-tet problem of the same cantilever family, K assembled,
+    load and Dirichlet applied by the oracle.  One `step()` = the reference's assembly loop over a slice of CPU_SLICE cells + CPU_ITERS
+    Jacobi-PCG iterations (CSC SpMV + vector passes) — and the extrapolation of both to the bench workload."""
+
+    def __init__(self, pkg, workload):
+        from oracle import c_oracle
+        self.co = c_oracle
+        self.workload = workload
+        self.dims = WORKLOADS[CPU_MESH]
+        nn, self.ne_w, self.nnz_w = structured_counts(WORKLOADS[workload])
+        self.n_w = 3 * nn
+        pts, cells, fixed, load = make_problem(pkg, self.dims)
+        self.lam, self.mu = pkg.create_material_model(1.0, 0.3)
+        t0 = time.perf_counter()
+        self.cp = cp = c_oracle.CProblem(pts, cells)             # first-touch DOFs + sorted CSC pattern
+        self.setup_s = time.perf_counter() - t0
+        cp.assemble(lam_mu=(self.lam, self.mu))                  # (q,i,j) loops + sorted-merge assembly, all cells (K for the PCG sample)
+        self.full_assemble_s = cp.t["assemble"]
+        cp.apply_force(load, [0.0, 0.0, -1.0])
+        pres0 = (cp.node_first_dof[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1)
+        cp.apply_dirichlet(pres0)
+        self.scratch = np.zeros(cp.nnz)
+        self.slice = min(CPU_SLICE, cp.ne)
+        self.iters_workload = self._iterations_of_workload()
+        _, _, _, _ = cp.pcg(TOL, 0)                              # init cost of the PCG call (diagonal extraction, r0, z0): subtracted below
+        self.pcg_init_s = cp.t["pcg"]
+
+    def _iterations_of_workload(self):
+        """Iteration count of the same Jacobi-PCG on the bench workload (the CPU cannot afford to find it: frozen from the converged
+        B200 runs, which agree with the oracle's count to ±2 wherever both exist — C1, C2, 200k, 1M tets)."""
+        try:
+            return int(json.load(open(GOLDEN_FULLSIZE))[self.workload]["niter"])
+        except Exception:
+            return None
+
+    def step(self):
+        import ctypes as C
+        cp, co = self.cp, self.co
+        mode, par, dens = cp._mat(lam_mu=(self.lam, self.mu))
+        t0 = time.perf_counter()
+        rc = cp.lib.oracle_assemble(C.c_int64(self.slice), cp.npc, co._i(cp.cells), co._d(cp.points), co._i(cp.cell_dofs), mode, co._d(par), co._d(dens),
+                                    C.c_int64(cp.n), co._i(cp.colptr), co._i(cp.rowval), co._d(self.scratch))
+        t_asm = time.perf_counter() - t0
+        assert rc == 0
+        _, k, _, _ = cp.pcg(TOL, CPU_ITERS)
+        t_it = max(cp.t["pcg"] - self.pcg_init_s, 1e-9) / max(k, 1)
+        return {"assemble_s": t_asm, "assemble_elements_per_s": self.slice / t_asm, "pcg_s_per_iteration": t_it, "iterations_run": int(k)}
+
+    def extrapolate(self, s, iterations=None):
+        it = iterations or self.iterations_workload()
+        scale = self.nnz_w / float(self.cp.nnz)
+        t_asm = self.ne_w / s["assemble_elements_per_s"]
+        t_pcg = it * s["pcg_s_per_iteration"] * scale
+        t_energy = s["pcg_s_per_iteration"] * scale            # one more SpMV-sized pass
+        return {"seconds_per_step": t_asm + t_pcg + t_energy, "assemble_seconds": t_asm, "pcg_seconds": t_pcg, "pcg_iterations": it,
+                "pcg_s_per_iteration_at_workload": s["pcg_s_per_iteration"] * scale, "nnz_scale": scale,
+                "value": self.ne_w / (t_asm + t_pcg + t_energy)}
+
+    def iterations_workload(self):
+        if self.iters_workload is None:
+            raise SystemExit("bench.py: no frozen iteration count for workload %s (tests/golden/fullsize_c3.json)" % self.workload)
+        return self.iters_workload
+
+    def describe(self, s, ex):
+        d = self.dims
+        return ("C restatement of the reference's loops (oracle/oracle.c; not Julia), 1 core like the reference (TopOptEval.jl has no threading). "
+                "Sampled: assembly of %d cells of the %dx%dx%d-cube cantilever (%d tets) = %.0f el/s; %d Jacobi-PCG iterations on its assembled, "
+                "constrained K (nnz %d) = %.4f s/iteration.  Extrapolated to %s: assembly %d cells / rate = %.0f s; PCG %d iterations (count of "
+                "the converged B200 solve) x s/iteration x nnz ratio %.2f = %.0f s; one step = %.0f s"
+                % (self.slice, d[0], d[1], d[2], self.cp.ne, s["assemble_elements_per_s"], s["iterations_run"], self.cp.nnz, s["pcg_s_per_iteration"],
+                   self.workload, self.ne_w, ex["assemble_seconds"], ex["pcg_iterations"], ex["nnz_scale"], ex["pcg_seconds"], ex["seconds_per_step"]))
+
+
+def run_reference(args, pkg, prog):
+    if prog.rank != 0:
         return
-    dims = CPU_SAMPLE
+    prog.at("cpu set-up (%s problem, untimed)" % CPU_MESH)
+    cs = CpuSample(pkg, args.workload)
+    prog.at("cpu warm-up")
     for _ in range(args.warmup):
-        cpu_step(pkg, dims)
+        cs.step()
+    prog.at("cpu timed steps")
     t0 = time.perf_counter()
+    acc = {"assemble_s": 0.0, "pcg_s_per_iteration": 0.0}
     last = None
     for _ in range(args.steps):
-        last = cpu_step(pkg, dims)
+        last = cs.step()
+        acc["assemble_s"] += last["assemble_s"]; acc["pcg_s_per_iteration"] += last["pcg_s_per_iteration"]
     dt = time.perf_counter() - t0
-    ne = last["ne"]
-    value = ne * args.steps / dt
-    sample = ("%dx%dx%d-cube cantilever = %d tets (%d DOFs), full path incl. DOF numbering + pattern, PCG to 1e-8 in %d iterations; "
-              "C restatement of the reference's loops (oracle/oracle.c), not Julia" % (dims + (ne, last["ndofs"], last["niter"])))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps,
+    mean = {"assemble_elements_per_s": cs.slice * args.steps / acc["assemble_s"], "pcg_s_per_iteration": acc["pcg_s_per_iteration"] / args.steps,
+            "iterations_run": last["iterations_run"]}
+    ex = cs.extrapolate(mean)
+    sample = cs.describe(mean, ex)
+    line = {"impl": "reference", "metric": METRIC, "value": ex["value"], "unit": "elements/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "bounded CPU sample of the cantilever workload: " + sample, "tolerance": TOL},
-            "cpu_baseline": {"value": value, "unit": "elements/s", "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "stages": {"assemble_elements_per_s": last["assemble_elements_per_s"], "pcg_seconds": last["stage_seconds"]["pcg"],
-                       "pcg_iterations": last["niter"], "setup_seconds": last["stage_seconds"]["setup"]}}
-    print(json.dumps(line), flush=True)
-
-
-def run_guarded(fn, timeout_s, on_failure):
-    """Runs the optional `fn()` with a deadline.  Returns None if there is nothing to run, True if it finished, False if it raised —
-    in which case `on_failure(reason)` has been called.  If `fn` is still running after `timeout_s` (a collective that never returns
-    cannot be cancelled), a watchdog thread calls `on_failure` and ends the PROCESS with exit code 0: the caller's results are out,
-    there is nothing left worth a hang."""
-    if fn is None:
-        return None
-    finished = threading.Event()
-
-    def watchdog():
-        if not finished.wait(timeout_s):
-            try:
-                on_failure("timed out after %.0f s" % timeout_s)
-            finally:
-                sys.stdout.flush()
-                os._exit(0)
-
-    threading.Thread(target=watchdog, daemon=True).start()
-    try:
-        fn()
-    except BaseException as ex:  # noqa: BLE001 — an optional extra must never cost the headline line
-        finished.set()
-        on_failure("%s: %s" % (type(ex).__name__, str(ex)[:300]))
-        return False
-    finished.set()
-    return True
+            "dtype": "f64", "data": "synthetic", "config": static_config(args),
+            "cpu_baseline": {"value": ex["value"], "unit": "elements/s", "cores": 1, "kind": "port", "sample": sample, "extrapolation": ex},
+            "e2e": {"value": ex["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "metric_parts": {"elements_assembled_per_s": mean["assemble_elements_per_s"], "pcg_seconds_to_1e-8": ex["pcg_seconds"],
+                             "pcg_iterations": ex["pcg_iterations"]},
+            "note": "ms_per_step is the measured duration of one bounded sample step; value is the extrapolated whole-step throughput on the "
+                    "bench workload (see cpu_baseline.sample); set-up (DOF numbering + pattern, %.1f s at 1M tets) is outside value in both arms" % cs.setup_s}
+    prog.emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------
-def run_b200(args, pkg):
+def run_b200(args, pkg, prog):
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,18 +292,19 @@ def run_b200(args, pkg):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
+        prog.at("init_process_group")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback")
     dims = WORKLOADS[args.workload]
+    prog.at("mesh generation")
     pts, cells, fixed, load = make_problem(pkg, dims)
-    # step inputs live in pinned host memory
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()        # step inputs live in pinned host memory
     pts, cells = pin(pts), pin(cells)
     lam, mu = pkg.create_material_model(1.0, 0.3)
     F = [0.0, 0.0, -1.0]
     mf = bool(args.matrix_free)
-
+    prog.at("create context")
     ctx = pkg.parallel.create_distributed_context(dist, local_rank) if world > 1 else pkg.Context(local_rank)
 
     def setup():
@@ -202,26 +312,21 @@ def run_b200(args, pkg):
         ctx.build_dofs()
         ctx.build_pattern()
 
-    verbose = os.environ.get("TOE_BENCH_VERBOSE") == "1"
-
-    def say(*a):
-        if verbose:
-            print("[rank %d %.3f]" % (rank, time.perf_counter()), *a, file=sys.stderr, flush=True)
-
-    def step():
-        say("step: assemble")
+    def step(tag):
+        prog.at(tag + ": assemble")
         if mf:
             ctx.set_material_lame(lam, mu)
         else:
             ctx.assemble_lame(lam, mu)
         ctx.add_nodal_force(load, F)
-        say("step: dirichlet")
         ctx.apply_dirichlet(pres)
-        say("step: solve")
+        prog.at(tag + ": solve")
         st = ctx.solve_pcg(TOL, TOL, ITMAX, matrix_free=mf)
-        say("step: solved", st["niter"], st["converged"], st["solve_seconds"])
         e, c, _ = ctx.energy()
-        say("step: energy", e)
+        prog.at(tag + ": done", st["niter"], st["converged"], "%.3f s" % st["solve_seconds"], e)
+        if not st["converged"] or st["breakdown"]:
+            prog.partial.update(failed_step=tag, niter=int(st["niter"]), breakdown=int(st["breakdown"]), rel_res_l2=st["rel_res_l2"], energy=e)
+            prog.fail("PCG did not converge in %s (niter=%d, breakdown=%d)" % (tag, st["niter"], st["breakdown"]), 4)
         return st, e, c
 
     def barrier():
@@ -237,202 +342,111 @@ def run_b200(args, pkg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    prog.at("set-up")
     setup()
     nfd = ctx.node_dofs()
     pres = np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1))
     ne_total = cells.shape[0]
 
-    def any_rank(flag):
-        if dist is None:
-            return bool(flag)
-        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return bool(t.item())
-
     # ---- device-resident arm: W warm-up steps, then exactly K timed steps -------------------------------------
-    # Partitioned runs only: a set-up whose solves break down (open item 2) is discarded — mesh re-partitioned,
-    # warm-ups and timed steps repeated — at most twice; `measurement_attempts` in the JSON line says how often that happened.
-    # A timed region is only ever reported if every one of its K steps converged.
-    def measure():
-        bad = False
-        for w in range(args.warmup):
-            stw, _, _ = step()
-            if not stw["converged"]:
-                bad = True
-                print("bench.py: warm-up step %d did not converge (niter=%d, breakdown=%d)" % (w, stw["niter"], stw["breakdown"]), file=sys.stderr, flush=True)
-        if any_rank(bad):
-            return None
-        sampler = ClockSampler(local_rank)
-        barrier()
-        launches0 = ctx.timings()["kernel_launches"]
-        sampler.start()
-        ctx.timer_start()
-        t0 = time.perf_counter()
-        acc = {"assemble": 0.0, "solve": 0.0, "spmv": 0.0, "energy": 0.0, "loads": 0.0, "dirichlet": 0.0}
-        st = e = c = None
-        restarts = 0
-        for _ in range(args.steps):
-            st, e, c = step()
-            restarts += int(st.get("restarts", 0))
-            if not st["converged"] or st["breakdown"]:
-                bad = True
-            tm = ctx.timings()
-            acc["assemble"] += tm["assemble"]; acc["solve"] += tm["solve"]; acc["energy"] += tm["energy"]
-            acc["loads"] += tm["loads"]; acc["dirichlet"] += tm["dirichlet"]; acc["spmv"] += st["spmv_seconds"]
-        dev_s = ctx.timer_stop()
-        barrier()
-        wall_s = time.perf_counter() - t0
-        clocks = sampler.stop()
-        launches = ctx.timings()["kernel_launches"] - launches0
-        if any_rank(bad):
-            print("bench.py: a timed step did not converge (niter=%d, breakdown=%d, rel_res=%g)" % (st["niter"], st["breakdown"], st["rel_res_l2"]), file=sys.stderr, flush=True)
-            return None
-        return dict(st=st, e=e, c=c, restarts=restarts, stage_acc=acc, dev_s=max_over_ranks(dev_s), wall_s=max_over_ranks(wall_s), clocks=clocks, launches=launches)
-
-    attempts = 0
-    m = None
-    while m is None:
-        attempts += 1
-        m = measure()
-        if m is None:
-            if world == 1 or attempts >= 3:
-                raise SystemExit("bench.py: PCG did not converge in the timed region (attempt %d) — no number reported" % attempts)
-            setup()
-    st, e, c, restarts, stage_acc = m["st"], m["e"], m["c"], m["restarts"], m["stage_acc"]
-    dev_s, wall_s, clocks, launches = m["dev_s"], m["wall_s"], m["clocks"], m["launches"]
+    for w in range(args.warmup):
+        step("warm-up %d" % w)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = ctx.timings()["kernel_launches"]
+    sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    acc = {"assemble": 0.0, "solve": 0.0, "spmv": 0.0, "energy": 0.0, "loads": 0.0, "dirichlet": 0.0}
+    iters = []
+    st = e = c = None
+    for k in range(args.steps):
+        st, e, c = step("timed %d" % k)
+        iters.append(int(st["niter"]))
+        tm = ctx.timings()
+        for key in ("assemble", "solve", "energy", "loads", "dirichlet"):
+            acc[key] += tm[key]
+        acc["spmv"] += st["spmv_seconds"]
+    dev_s = ctx.timer_stop()
+    barrier()
+    wall_s = max_over_ranks(time.perf_counter() - t0)
+    dev_s = max_over_ranks(dev_s)
+    clocks = sampler.stop()
+    launches = ctx.timings()["kernel_launches"] - launches0
     value = ne_total * args.steps / dev_s
+    prog.partial.update(value=value, ms_per_step=1e3 * dev_s / args.steps, pcg_iterations=iters[-1])
 
     # dominant kernel (SpMV inside PCG): live CUDA-event timing of back-to-back launches on the library's stream
+    prog.at("operator timing")
     spmv_s, spmv_bytes = ctx.time_spmv(matrix_free=mf, reps=20)
     spmv_s = max_over_ranks(spmv_s)
     peaks, peak_src = measured_peaks()
     sizes = ctx.local_sizes() if world > 1 else None
 
     # ---- end-to-end arm: host buffers in, u + energies out, every step ---------------------------------------
-    def e2e_step():
+    def e2e_step(tag):
+        prog.at(tag + ": set-up")
         setup()
-        st_, e_, c_ = step()
+        st_, e_, c_ = step(tag)
         u = ctx.solution()
         return st_, e_, c_, u
 
-    e2e_step()                                            # one warm-up (allocations are reused afterwards)
+    e2e_step("e2e warm-up")                               # allocations are reused afterwards
     tm_setup = ctx.timings()
-    e2e_steps = min(args.steps, 3)                        # bounded: the e2e arm repeats the full path incl. setup
+    e2e_steps = min(args.steps, 3)                        # bounded: the e2e arm repeats the full path incl. set-up
     barrier()
     t0 = time.perf_counter()
-    e2e_retries = 0
-    e2e_restarts = 0                                      # CG restarts inside toe_solve_pcg (partitioned runs): every e2e step is a first solve after a set-up
-    for _ in range(e2e_steps):
-        for attempt in range(3):                          # partitioned runs: a step whose solve broke down is repeated INSIDE the timed region
-            st2, e2, c2, u = e2e_step()
-            e2e_restarts += int(st2.get("restarts", 0))
-            if not any_rank(not st2["converged"]) or world == 1:
-                break
-            e2e_retries += 1
+    for k in range(e2e_steps):
+        st2, e2, c2, u = e2e_step("e2e %d" % k)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    # the end-to-end arm must have done the same work and reached the same answer as the device-resident arm
-    e2e_invalid = None
-    if (not st2["converged"]) or abs(int(st2["niter"]) - int(st["niter"])) > 2 or abs(e2 - e) > 1e-8 * abs(e) or not np.all(np.isfinite(u)):
-        e2e_invalid = ("end-to-end step disagrees with the device-resident step (iters %d vs %d, energy %r vs %r, converged %r)"
-                       % (st2["niter"], st["niter"], e2, e, bool(st2["converged"])))
-        print("bench.py: " + e2e_invalid, file=sys.stderr, flush=True)
-    # extra, not part of `value`: the same solve with the two-level preconditioner, run in a CHILD process so
-    # that nothing it does can touch the measurements above (this ctx stays alive; the GPU has room for both)
+    if abs(int(st2["niter"]) - int(st["niter"])) > 2 or abs(e2 - e) > 1e-8 * abs(e) or not np.all(np.isfinite(u)):
+        prog.fail("end-to-end step disagrees with the device-resident step (iterations %d vs %d, energy %r vs %r)" % (st2["niter"], st["niter"], e2, e), 5)
+
+    # extra, never in `value`: the same solve with the two-level preconditioner in a CHILD process
     two_level = None
-    variants = None
-    if world == 1 and not args.no_two_level and rank == 0:
-        two_level = two_level_probe_in_child(args, e, stage_acc["solve"] / args.steps)
-    if world == 1 and not getattr(args, "no_variants", False) and not mf and rank == 0:
-        variants = variant_probes_in_children(args)
+    if world == 1 and not args.no_two_level:
+        prog.at("two-level probe (child process)")
+        two_level = two_level_probe_in_child(args, e, acc["solve"] / args.steps)
 
     h2d = pts.nbytes + cells.nbytes + load.nbytes + pres.nbytes
     d2h = u.nbytes + 2 * 8 + 128
-    info = {"ndofs": ctx.ndofs, "nnz": ctx.nnz, "transport": ctx.comm_info()["transport"]}      # read now: the probes below re-set-up the ctx
+    info = {"ndofs": ctx.ndofs, "nnz": ctx.nnz, "transport": ctx.comm_info()["transport"]}
+    pcg_s = acc["solve"] / args.steps
+    asm_rate = ne_total * args.steps / acc["assemble"] if acc["assemble"] > 0 else None
 
     line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: structured-tet cantilever %dx%dx%d cubes x 6 = %d Tet4, %d DOFs, nnz %d; E=1, nu=0.3, solid densities, clamp x=0, "
-                                   "tip load -1 z; Jacobi-PCG atol=rtol=1e-8 (Krylov.jl M-norm)" % ((args.workload,) + dims + (ne_total, info["ndofs"], info["nnz"])),
-                       "operator": "matrix-free EbE" if mf else "assembled block-CSR", "parallelism": "dd%d" % world,
-                       "exchange": info["transport"],
-                       "l2": "inputs exceed L2 (K = %.2f GB vs 126 MB); no flush needed" % (info["nnz"] * 8 / 1e9),
-                       "wall_ms_per_step": 1e3 * wall_s / args.steps, "measurement_attempts": attempts},
+            "dtype": "f64", "data": "synthetic", "config": static_config(args),
+            "metric_parts": {"elements_assembled_per_s": asm_rate, "pcg_seconds_to_1e-8": pcg_s, "pcg_iterations": iters[-1],
+                             "criterion": "Krylov.jl cg: sqrt(r'Mr) <= atol + rtol*sqrt(r0'Mr0), atol = rtol = 1e-8 (RobustSolver.jl:294-305)"},
             "clocks": clocks,
-            "e2e": {"value": None if e2e_invalid else ne_total * e2e_steps / e2e_s, "invalid": e2e_invalid, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "repeated_steps": e2e_retries, "pcg_restarts": e2e_restarts, "pcg_iterations": int(st2["niter"]), "energy": e2,
+            "e2e": {"value": ne_total * e2e_steps / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pcg_iterations": int(st2["niter"]), "energy": e2,
                     "path": "host mesh (pinned) -> toe_set_mesh -> build_dofs -> build_pattern -> assemble -> loads -> apply! -> PCG -> energy -> u to host"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_ebe_tile+k_ebe_nodes" if mf else "k_spmv_bsr_pipe", "bound": "hbm", "achieved": spmv_bytes / spmv_s / 1e9, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": spmv_bytes / spmv_s / 1e9 / peaks["hbm_gbs"], "traffic": profile_traffic(mf), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": spmv_bytes, "launch_seconds": spmv_s,
-                         "share_of_step": stage_acc["spmv"] / dev_s},
-            "stages": {"assemble_elements_per_s": ne_total * args.steps / stage_acc["assemble"] if stage_acc["assemble"] > 0 else None,
-                       "assemble_ms": 1e3 * stage_acc["assemble"] / args.steps, "pcg_seconds": stage_acc["solve"] / args.steps,
-                       "pcg_iterations": int(st["niter"]), "pcg_converged": bool(st["converged"]), "pcg_rel_res_l2": st["rel_res_l2"], "pcg_restarts": restarts,
-                       "spmv_gbs": spmv_bytes / spmv_s / 1e9, "energy_ms": 1e3 * stage_acc["energy"] / args.steps,
-                       "energy": e, "compliance": c, "local_sizes": sizes,
+                         "algorithmic_bytes_per_launch": spmv_bytes, "launch_seconds": spmv_s, "share_of_step": acc["spmv"] / dev_s},
+            "stages": {"assemble_ms": 1e3 * acc["assemble"] / args.steps, "loads_ms": 1e3 * acc["loads"] / args.steps, "dirichlet_ms": 1e3 * acc["dirichlet"] / args.steps,
+                       "pcg_seconds": pcg_s, "pcg_iterations_per_step": iters, "pcg_converged": True, "pcg_rel_res_l2": st["rel_res_l2"],
+                       "spmv_gbs": spmv_bytes / spmv_s / 1e9, "energy_ms": 1e3 * acc["energy"] / args.steps,
+                       "energy": e, "compliance": c, "local_sizes": sizes, "exchange": info["transport"], "ndofs": info["ndofs"], "nnz_local": info["nnz"],
+                       "wall_ms_per_step": 1e3 * wall_s / args.steps,
                        "setup_ms": {k: 1e3 * tm_setup[k] for k in ("set_mesh", "build_dofs", "build_pattern")},
-                       "two_level_preconditioner": two_level, "variants": variants},
+                       "two_level_preconditioner": two_level},
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_step(pkg, CPU_SAMPLE)
-            line["cpu_baseline"] = {"value": cb["ne"] / cb["seconds"], "unit": "elements/s", "cores": 1, "kind": "port",
-                                    "sample": "%dx%dx%d-cube cantilever = %d tets, full path in %.1f s (assemble %.0f el/s, PCG %d it); C restatement of the "
-                                              "reference's loops, single core like the reference (no threading in TopOptEval.jl); not Julia"
-                                              % (CPU_SAMPLE + (cb["ne"], cb["seconds"], cb["assemble_elements_per_s"], cb["niter"]))}
-
-    # ---- N > 1 extra, never part of `value`: the opt-in exchange transports on the same partitioned workload ----------------------------
-    # Everything the line needs is measured by now.  The probes re-set-up the ctx with another transport (first time on real NCCL /
-    # NVLink for the all-gather one), so they run under a watchdog: whatever happens in there — an exception, a collective that never
-    # returns — rank 0 still prints the line (with what the probes delivered so far) and every rank leaves.
-    emit_lock, emitted = threading.Lock(), []
-
-    def emit(extra):
-        with emit_lock:                                              # exactly ONE line, whoever gets here first (main thread or watchdog)
-            if emitted:
-                return
-            emitted.append(True)
-            if line is not None:
-                line["stages"]["exchange_transports"] = extra
-                print(json.dumps(line), flush=True)
-
-    probes = {}
-
-    def transport_probes():
-        for name, env in (("nccl-allgather", {"TOE_DIST_XCHG": "allgather"}), ("peer-memory", {"TOE_DIST_P2P": "1"})):
-            if name == info["transport"]:
-                continue
-            os.environ.update(env)
-            try:
-                setup()
-                got = ctx.comm_info()["transport"]
-                stw, _, _ = step()                                   # first solve after a set-up: warm-up
-                barrier()
-                ctx.timer_start()
-                stp, ep, _ = step()
-                dev = ctx.timer_stop()
-                barrier()
-                probes[name] = {"transport": got, "ms_per_step": 1e3 * max_over_ranks(dev), "pcg_seconds": ctx.timings()["solve"],
-                                "pcg_iterations": int(stp["niter"]), "converged": bool(stp["converged"]),
-                                "restarts": int(stw.get("restarts", 0)) + int(stp.get("restarts", 0)), "energy": ep,
-                                "energy_rel_diff_vs_default": abs(ep - e) / abs(e)}
-            finally:
-                for k in env:
-                    os.environ.pop(k, None)
-
-    clean = run_guarded(transport_probes if (world > 1 and not getattr(args, "no_transport_probes", False)) else None, 150.0,
-                        lambda why: emit(dict(probes, error=why)))
-    if clean is None:
-        emit(None)                                                   # nothing to probe (single GPU or switched off)
-    elif clean:
-        emit(dict(probes, note="opt-in transports, one timed step each after a fresh set-up + warm-up step; never in `value`"))
-    else:
-        os._exit(0)                                                  # a probe failed: the line is out (emit ran), the ctx may be unusable — leave without teardown
+            prog.at("cpu baseline (bounded sample)")
+            cs = CpuSample(pkg, args.workload)
+            s = cs.step()
+            ex = cs.extrapolate(s, iterations=iters[-1])
+            line["cpu_baseline"] = {"value": ex["value"], "unit": "elements/s", "cores": 1, "kind": "port", "sample": cs.describe(s, ex), "extrapolation": ex}
+    prog.at("done")
+    prog.emit(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -464,7 +478,7 @@ def two_level_probe(args, pkg):
 def two_level_probe_in_child(args, energy_jacobi, jacobi_pcg_seconds):
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "two-level-probe", "--workload", args.workload] + (["--matrix-free"] if args.matrix_free else [])
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if r.returncode != 0 or not lines:
             return {"error": ("rc=%d " % r.returncode) + (r.stderr or r.stdout)[-300:]}
@@ -477,35 +491,13 @@ def two_level_probe_in_child(args, energy_jacobi, jacobi_pcg_seconds):
         return {"error": str(ex)[:300]}
 
 
-def variant_probes_in_children(args):
-    """N=1 extra, not part of `value`: the opt-in kernel variants (ROWS assembly, pipelined matrix-free operator) timed next to their
-    defaults on the same workload by tools/variants_probe.py — one CHILD process per section, so that a kernel that has not met
-    real hardware yet can fault without touching the headline measurement (this process's ctx stays alive meanwhile)."""
-    size = {"C4_10M": "10M", "C3_1M": "1M", "200k": "200k", "toy": "toy"}.get(args.workload)
-    if size is None:
-        return None
-    out = {}
-    for key, section in (("assembly", "asm"), ("matrix_free_operator", "ebe")):
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "variants_probe.py"), size, "--only", section]
-        try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=150, cwd=ROOT)
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            if r.returncode != 0 or not lines:
-                out[key] = {"error": ("rc=%d " % r.returncode) + (r.stderr or r.stdout)[-300:]}
-            else:
-                out[key] = json.loads(lines[-1]).get(key)
-        except Exception as ex:  # noqa: BLE001 — an optional extra must never cost the headline number
-            out[key] = {"error": str(ex)[:300]}
-    out["note"] = "opt-in variants next to their defaults, separate processes; reported for comparison, never in `value`"
-    return out
-
-
 def profile_traffic(matrix_free):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/*.json), else None."""
-    p = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
-    if os.path.exists(p):
-        d = json.load(open(p))
-        return d.get("ebe" if matrix_free else "bsr", {}).get("dram_bytes_per_launch")
+    for name in ("r2_dominant_kernel.json", "r1_dominant_kernel.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            return d.get("ebe" if matrix_free else "bsr", {}).get("dram_bytes_per_launch")
     return None
 
 
@@ -519,16 +511,23 @@ def main():
     ap.add_argument("--matrix-free", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-two-level", action="store_true", help="skip the extra two-level-preconditioner solve reported in stages")
-    ap.add_argument("--no-transport-probes", action="store_true", help="N > 1: skip the opt-in exchange transports reported in stages.exchange_transports")
-    ap.add_argument("--no-variants", action="store_true", help="skip the opt-in kernel variants (child processes) reported in stages.variants")
+    ap.add_argument("--deadline", type=float, default=float(os.environ.get("TOE_BENCH_DEADLINE", "780")),
+                    help="seconds after which the run ends with an error line instead of hanging")
     args = ap.parse_args()
     import __graft_entry__ as graft
     pkg = graft.load_package()
-    if args.impl == "reference":
-        return run_reference(args, pkg)
     if args.impl == "two-level-probe":
         return two_level_probe(args, pkg)
-    return run_b200(args, pkg)
+    prog = Progress(args, int(os.environ.get("RANK", "0")))
+    prog.watchdog(args.deadline)
+    try:
+        return (run_reference if args.impl == "reference" else run_b200)(args, pkg, prog)
+    except SystemExit:
+        raise
+    except BaseException as ex:  # noqa: BLE001 — one JSON line whatever happens
+        import traceback
+        traceback.print_exc()
+        prog.fail("%s: %s" % (type(ex).__name__, str(ex)[:300]), 6)
 
 
 if __name__ == "__main__":

@@ -47,6 +47,10 @@ typedef struct toe_ctx toe_ctx;
                                      coarse grid over the mesh (≤ 6144 coarse unknowns); same stopping rule on sqrt(r'Mr).
                                      SolverConfig.preconditioner = :two_level in the shims; works on partitioned contexts too */
 
+#define TOE_PCG_L2_NORM       8   /* stop on ||r||_2 <= atol + rtol*||r0||_2 (r = the recurrence residual) instead of Krylov.jl's M-norm rule
+                                     (SURVEY §8(b) norm_kind; the reference prints this norm at RobustSolver.jl:468).  Jacobi only.
+                                     history / res0_M / res_M then hold l2 norms */
+
 typedef struct toe_pcg_stats {
     int64_t niter;            /* Krylov.jl stats.niter */
     int32_t converged;        /* Krylov.jl stats.solved: sqrt(r'Mr) <= atol + rtol*sqrt(r0'Mr0) */
@@ -58,9 +62,12 @@ typedef struct toe_pcg_stats {
     double  spmv_seconds;     /* niter x average operator time, measured on a few isolated launches after the solve */
     double  spmv_bytes;       /* algorithmic bytes of one operator application */
     int64_t kernel_launches;  /* kernels launched by this call */
-    int64_t restarts;         /* partitioned runs only: solves restarted after a CG breakdown (0 normally) */
+    int64_t restarts;         /* always 0 (round 1 restarted partitioned solves after a breakdown; removed, the field keeps the layout) */
     int64_t coarse_dofs;      /* TOE_PCG_TWO_LEVEL: size of the coarse space (0 otherwise) */
     double  precond_seconds;  /* TOE_PCG_TWO_LEVEL: device time spent building ZᵀKZ and its inverse (part of solve_seconds) */
+    double  true_res;         /* norm of f - K u recomputed after the solve, in the norm of the stopping test (M-norm with Jacobi, l2 with
+                                 TOE_PCG_L2_NORM or the two-level preconditioner).  A converged Jacobi solve whose true_res exceeds 1e4 x the
+                                 tolerance returns an error (corrupted iterates) */
 } toe_pcg_stats;
 
 typedef struct toe_timings {  /* device seconds of the last call of each stage (CUDA events) */

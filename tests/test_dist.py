@@ -71,7 +71,7 @@ def test_gloo_world2_host_plumbing(tmp_path):
 def test_reference_arm_prints_one_line_under_torchrun():
     """`bench.py --impl reference` launched like the B200 arm (torchrun, N=2): rank 0 alone works and prints."""
     r = _torchrun(2, ["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], 29534, timeout=280,
-                  env={"TOE_BENCH_CPU_SAMPLE": "24,8,4"})
+                  env={"TOE_BENCH_CPU_MESH": "tiny", "TOE_BENCH_CPU_SLICE": "2000", "TOE_BENCH_CPU_ITERS": "5"})
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -79,3 +79,10 @@ def test_reference_arm_prints_one_line_under_torchrun():
     assert d["impl"] == "reference" and d["unit"] == "elements/s" and d["value"] > 0 and d["n_gpus"] == 2
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # same metric / config as the B200 arm prints for the same arguments, and the extrapolation is spelled out
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["metric"] == bench.METRIC and d["config"] == bench.static_config(types.SimpleNamespace(workload="C4_10M", matrix_free=False, gpus=2))
+    ex = d["cpu_baseline"]["extrapolation"]
+    assert ex["pcg_iterations"] == 13689 and abs(ex["value"] - d["value"]) < 1e-9 and "Extrapolated" in d["cpu_baseline"]["sample"]

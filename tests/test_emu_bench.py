@@ -13,6 +13,12 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import emu_support  # noqa: E402
 
 
+def _args(**kw):
+    d = dict(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=False, no_cpu_baseline=True, no_two_level=False, deadline=600.0)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
 @pytest.mark.parametrize("mf", [False, True])
 def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
     import torch
@@ -22,7 +28,7 @@ def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
-    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=mf, no_cpu_baseline=True, no_two_level=mf, no_variants=False)
+    args = _args(matrix_free=mf, no_two_level=mf)
     def probe_in_process(a, energy_jacobi, jacobi_s):             # the child process of the real bench, in-process on the emulated build
         b2 = io.StringIO()
         with redirect_stdout(b2):
@@ -31,56 +37,64 @@ def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
         d2["energy_rel_diff_vs_jacobi"] = abs(d2["energy"] - energy_jacobi) / abs(energy_jacobi)
         return d2
     monkeypatch.setattr(bench, "two_level_probe_in_child", probe_in_process)
-    monkeypatch.setattr(bench, "variant_probes_in_children", lambda a: {"assembly": {"stub": True}, "note": "stubbed: the children need a GPU"})
     buf = io.StringIO()
     with emu_support.emulated(pkg, lib), redirect_stdout(buf):
-        bench.run_b200(args, pkg)
+        bench.run_b200(args, pkg, bench.Progress(args, 0))
     lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
-                "config", "clocks", "e2e", "gpu_launches", "roofline", "stages"):
+                "config", "clocks", "e2e", "gpu_launches", "roofline", "stages", "metric_parts"):
         assert key in d, key
+    assert "error" not in d
+    assert d["metric"] == json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "BASELINE.json")))["metric"]
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["unit"] == "elements/s" and d["dtype"] == "f64"
     assert d["value"] > 0 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
-    assert "workload" in d["config"] and d["config"]["measurement_attempts"] == 1
+    assert d["config"] == bench.static_config(args)               # the reference arm prints the very same dict
     e2e = d["e2e"]
-    assert e2e["value"] > 0 and e2e["invalid"] is None and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and e2e["repeated_steps"] == 0
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
-    assert d["stages"]["pcg_converged"] and d["stages"]["pcg_iterations"] > 0 and d["stages"]["energy"] > 0
-    assert (d["stages"]["variants"] is None) == mf
+    mp = d["metric_parts"]
+    assert mp["elements_assembled_per_s"] is None or mp["elements_assembled_per_s"] > 0
+    assert mp["pcg_seconds_to_1e-8"] > 0 and mp["pcg_iterations"] > 0
+    assert d["stages"]["pcg_converged"] and d["stages"]["pcg_iterations_per_step"] == [mp["pcg_iterations"]] * 2 and d["stages"]["energy"] > 0
     tl = d["stages"]["two_level_preconditioner"]
-    assert (mf and tl is None) or "error" not in tl and tl["converged"] and tl["pcg_iterations"] < d["stages"]["pcg_iterations"] and tl["energy_rel_diff_vs_jacobi"] < 1e-6
+    assert (mf and tl is None) or "error" not in tl and tl["converged"] and tl["pcg_iterations"] < mp["pcg_iterations"] and tl["energy_rel_diff_vs_jacobi"] < 1e-6
 
 
-@pytest.mark.parametrize("section,key", [("asm", "assembly"), ("ebe", "matrix_free_operator")])
-def test_variants_probe_sections_on_emulated_build(monkeypatch, capsys, section, key):
-    """tools/variants_probe.py --only <section> (the child processes of bench.py's stages.variants) driven in-process on the emulated
-    build: the tool itself has no CPU route — the library handle is swapped here, by the test."""
-    import importlib.util
+def test_bench_fails_fast_with_one_error_line(monkeypatch):
+    """A step that does not converge ends the run at once: one JSON line with "error" and the stage, non-zero exit — no retries."""
+    import torch
     pkg, lib = emu_support.load_emu()
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("variants_probe_under_test", os.path.join(root, "tools", "variants_probe.py"))
-    mod = importlib.util.module_from_spec(spec)
-    monkeypatch.setattr(sys, "argv", ["variants_probe.py", "toy", "--only", section])
-    monkeypatch.chdir(root)
-    with emu_support.emulated(pkg, lib):
-        spec.loader.exec_module(mod)
-        capsys.readouterr()
-        mod.main()
-    out = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
-    assert key in out and out["ne"] == 288
-    if section == "asm":
-        assert out[key]["rows"]["max_rel_diff_Kx_vs_gather"] < 1e-13 and out[key]["rows"]["ms_min"] > 0
-    else:
-        assert out[key]["pipe"]["bit_identical_to_tile"] is True and out[key]["pipe"]["ms"] > 0
+    import bench
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.setattr(bench, "ITMAX", 3)                        # cannot converge
+    codes = []
+
+    class Exit(Exception):
+        pass
+
+    def fake_exit(code):
+        codes.append(code)
+        raise Exit()
+    monkeypatch.setattr(bench.os, "_exit", fake_exit)
+    args = _args(no_two_level=True)
+    buf = io.StringIO()
+    with emu_support.emulated(pkg, lib), redirect_stdout(buf), pytest.raises(Exit):
+        bench.run_b200(args, pkg, bench.Progress(args, 0))
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
+    assert codes == [4] and len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] is None and "did not converge" in d["error"] and d["stage"].startswith("warm-up 0") and d["partial"]["niter"] == 3
 
 
 def test_bench_partitioned_flow_on_emulated_build(monkeypatch):
-    """The N > 1 control flow of bench.py (re-measurement loop, e2e arm with restarts, the guarded transport probes) cannot meet real
-    NCCL here; it is driven with WORLD_SIZE=2 against ONE emulated rank (a 1-rank communicator, torch.distributed stubbed) so that
-    every statement of that path executes at least once: the line must come out once, complete, with the probes' entries."""
+    """The N > 1 control flow of bench.py cannot meet real NCCL here; it is driven with WORLD_SIZE=2 against ONE emulated rank (a 1-rank
+    communicator, torch.distributed stubbed) so that every statement of that path executes at least once."""
     import torch
     import torch.distributed as tdist
     pkg, lib = emu_support.load_emu()
@@ -100,18 +114,12 @@ def test_bench_partitioned_flow_on_emulated_build(monkeypatch):
         ctx.comm_init(1, 0, pkg.Context.comm_unique_id())
         return ctx
     monkeypatch.setattr(pkg.parallel, "create_distributed_context", one_rank_context)
-    args = types.SimpleNamespace(gpus=2, steps=1, warmup=1, impl="b200", workload="toy", matrix_free=False, no_cpu_baseline=True, no_two_level=True,
-                                 no_variants=True, no_transport_probes=False)
+    args = _args(gpus=2, steps=1, no_two_level=True)
     buf = io.StringIO()
     with emu_support.emulated(pkg, lib), redirect_stdout(buf):
-        bench.run_b200(args, pkg)
+        bench.run_b200(args, pkg, bench.Progress(args, 0))
     lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["n_gpus"] == 2 and d["config"]["parallelism"] == "dd2" and d["config"]["measurement_attempts"] == 1
-    assert d["e2e"]["invalid"] is None and d["e2e"]["pcg_restarts"] == 0 and d["stages"]["pcg_restarts"] == 0
-    assert "cpu_baseline" not in d and d["stages"]["local_sizes"] is not None
-    xt = d["stages"]["exchange_transports"]
-    assert "error" not in xt and set(xt) == {"nccl-allgather", "peer-memory", "note"}
-    for name in ("nccl-allgather", "peer-memory"):
-        assert xt[name]["converged"] and xt[name]["pcg_iterations"] == d["stages"]["pcg_iterations"] and xt[name]["energy_rel_diff_vs_default"] < 1e-12
+    assert "error" not in d and d["n_gpus"] == 2 and d["config"]["parallelism"] == "dd2"
+    assert "cpu_baseline" not in d and d["stages"]["local_sizes"] is not None and d["e2e"]["value"] > 0

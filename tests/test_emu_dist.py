@@ -110,7 +110,7 @@ def test_partitioned_equals_single_ctx(emu, world, dims, simp, mf):
     r0 = ranks[0][-1]
     counts = np.bincount(r0["part"], minlength=world)
     assert counts.max() - counts.min() <= 1, counts
-    assert r0["transport"] == "nccl"
+    assert r0["transport"] == "nccl-allgather"                 # the default transport
     for rk in range(world):
         first, r = ranks[rk][0], ranks[rk][-1]
         # every rank returns the same global answer, re-setups are bit-reproducible, and it equals the unpartitioned solve
@@ -140,9 +140,9 @@ def test_peer_memory_exchange_protocol(emu, world, dims, monkeypatch):
     monkeypatch.setenv("EMU_JITTER", "1")
     prob = _problem(pkg, dims, False)
     nccl = _run_ranks(pkg, world, prob, False, repeats=1, tol=1e-9)
-    monkeypatch.setenv("TOE_DIST_P2P", "1")
+    monkeypatch.setenv("TOE_DIST_XCHG", "p2p")
     p2p = _run_ranks(pkg, world, prob, False, repeats=3, tol=1e-9)
-    assert p2p[0][-1]["transport"] == "peer-memory" and nccl[0][-1]["transport"] == "nccl"
+    assert p2p[0][-1]["transport"] == "peer-memory" and nccl[0][-1]["transport"] == "nccl-allgather"
     for rk in range(world):
         for rep in range(3):
             r = p2p[rk][rep]
@@ -152,13 +152,14 @@ def test_peer_memory_exchange_protocol(emu, world, dims, monkeypatch):
 
 @pytest.mark.parametrize("world,dims,simp,mf", [(2, (10, 4, 3), False, True), (4, (10, 4, 2), True, False), (8, (16, 4, 2), False, False)])
 def test_allgather_exchange_transport(emu, world, dims, simp, mf, monkeypatch):
-    """TOE_DIST_XCHG=allgather: one ncclAllGather per exchange carries every rank's packed interface values and its partial scalars.
-    Same arithmetic and summation order as the send/recv transport → bit-identical iterates, loads, diagonals and per-cell outputs;
-    re-set-ups on the same ctx reproduce."""
+    """The default transport — one ncclAllGather per exchange carries every rank's packed interface values and its partial scalars —
+    against the opt-in send/recv + allreduce transport (TOE_DIST_XCHG=sendrecv): same arithmetic and summation order → bit-identical
+    iterates, loads, diagonals and per-cell outputs; re-set-ups on the same ctx reproduce."""
     pkg, lib = emu
     prob = _problem(pkg, dims, simp)
+    monkeypatch.setenv("TOE_DIST_XCHG", "sendrecv")
     ref = _run_ranks(pkg, world, prob, mf, repeats=1, tol=1e-9)
-    monkeypatch.setenv("TOE_DIST_XCHG", "allgather")
+    monkeypatch.delenv("TOE_DIST_XCHG")
     ag = _run_ranks(pkg, world, prob, mf, repeats=2, tol=1e-9)
     assert ag[0][-1]["transport"] == "nccl-allgather" and ref[0][-1]["transport"] == "nccl"
     for rk in range(world):

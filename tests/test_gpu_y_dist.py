@@ -1,7 +1,6 @@
-"""N>1 path on real GPUs: partition invariance (N-GPU == 1-GPU == oracle) through tests/dist_worker.py under torchrun, both exchange
-transports; skipped when fewer than 2 (4) GPUs are visible.  The file name sorts after the single-GPU parity files on purpose: the
-partitioned path was hardened after the last multi-GPU run of round 1 (double-buffered staging, stream rendezvous, restart net),
-so under `-x` a surprise here must not hide the single-GPU parity results."""
+"""N>1 path on real GPUs: partition invariance (N-GPU == 1-GPU == oracle) through tests/dist_worker.py under torchrun: the default transport
+(one ncclAllGather per exchange) and the peer-memory kernel; skipped when fewer than 2 (4) GPUs are visible.  The file name sorts after
+the single-GPU parity files on purpose: under `-x` a surprise here must not hide the single-GPU parity results."""
 import pytest
 
 from test_dist import _ngpus, _torchrun
@@ -12,7 +11,7 @@ from test_dist import _ngpus, _torchrun
 def test_two_gpu_partition_invariance(dims, extra):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, ["tests/dist_worker.py", dims] + extra, 29531, env={"TOE_EXPECT_TRANSPORT": "nccl"})
+    r = _torchrun(2, ["tests/dist_worker.py", dims] + extra, 29531, env={"TOE_EXPECT_TRANSPORT": "nccl-allgather"})
     assert r.returncode == 0 and "DIST PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 

@@ -13,14 +13,14 @@ LIB_PATH = os.path.join(HERE, "libtopopt_b200.so")
 CSRC = os.path.join(HERE, "csrc")
 
 ASM_AUTO, ASM_ATOMIC, ASM_GATHER, ASM_ROWS = 0, 1, 2, 3
-PCG_MATRIX_FREE, PCG_NO_GRAPH, PCG_TWO_LEVEL = 1, 2, 4
+PCG_MATRIX_FREE, PCG_NO_GRAPH, PCG_TWO_LEVEL, PCG_L2_NORM = 1, 2, 4, 8
 
 
 class PcgStats(C.Structure):
     _fields_ = [("niter", C.c_int64), ("converged", C.c_int32), ("breakdown", C.c_int32),
                 ("res0_M", C.c_double), ("res_M", C.c_double), ("rel_res_l2", C.c_double),
                 ("solve_seconds", C.c_double), ("spmv_seconds", C.c_double), ("spmv_bytes", C.c_double),
-                ("kernel_launches", C.c_int64), ("restarts", C.c_int64), ("coarse_dofs", C.c_int64), ("precond_seconds", C.c_double)]
+                ("kernel_launches", C.c_int64), ("restarts", C.c_int64), ("coarse_dofs", C.c_int64), ("precond_seconds", C.c_double), ("true_res", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -336,9 +336,10 @@ class Context:
         return m.value
 
     # -- solve / post -------------------------------------------------------------------------------------
-    def solve_pcg(self, atol=1e-8, rtol=1e-8, itmax=10000, matrix_free=False, graph=True, history=False, two_level=False):
+    def solve_pcg(self, atol=1e-8, rtol=1e-8, itmax=10000, matrix_free=False, graph=True, history=False, two_level=False, l2_norm=False):
         st = PcgStats()
-        flags = (PCG_MATRIX_FREE if matrix_free else 0) | (0 if graph else PCG_NO_GRAPH) | (PCG_TWO_LEVEL if two_level else 0)
+        flags = ((PCG_MATRIX_FREE if matrix_free else 0) | (0 if graph else PCG_NO_GRAPH) | (PCG_TWO_LEVEL if two_level else 0)
+                 | (PCG_L2_NORM if l2_norm else 0))
         hist = np.zeros(min(itmax + 1, 1 << 20)) if history else None
         self._ck(self.lib.toe_solve_pcg(self.h, atol, rtol, itmax, flags, C.byref(st), _dp(hist), 0 if hist is None else hist.size))
         out = st.asdict()

@@ -69,9 +69,11 @@ struct CGScalars {
     int converged;
     int breakdown;
     int pad;
-    // single-reduction (Chronopoulos–Gear) recurrence used on partitioned runs: {γ, δ} double-buffered by iteration parity
-    double gd[2][2];
+    // single-reduction (Chronopoulos–Gear) recurrence used on partitioned runs: {γ, δ, ν = r'r (l2 criterion only), unused}
+    // double-buffered by iteration parity; the first 2 (3 with the l2 criterion) are summed over the ranks by the exchange
+    double gd[2][4];
     double alpha[2];
+    double res;        // residual in the norm of the stopping test at the last completed iteration (√(r'Mr) or ‖r‖₂)
 };
 
 struct DistState;   // dist.cu
@@ -272,16 +274,40 @@ __device__ __forceinline__ bool grid_sum_last_block(double block_val /*thread 0*
     return false;
 }
 
+// two sums with one ticket: the same (last) block holds both totals.  `partials` must hold 2*gridDim.x doubles.
+__device__ __forceinline__ bool grid_sum2_last_block(double v0, double v1 /*thread 0*/, double* partials, unsigned int* counter,
+                                                     double* sh, double* tot0, double* tot1) {
+    __shared__ bool is_last2;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = v0; partials[gridDim.x + blockIdx.x] = v1;
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last2 = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last2) return false;
+    __threadfence();
+    double s0 = 0.0, s1 = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) { s0 += __ldcg(&partials[i]); s1 += __ldcg(&partials[gridDim.x + i]); }
+    s0 = block_sum(s0, sh);
+    s1 = block_sum(s1, sh);
+    if (threadIdx.x == 0) { *tot0 = s0; *tot1 = s1; *counter = 0u; return true; }
+    return false;
+}
+
 // ---- PCG scalar recurrences (device side) -------------------------------------------------------------------
 __device__ __forceinline__ void cg_after_pAp(CGScalars* s, double pAp) {
     s->pAp = pAp;
     if (!(pAp > 0.0)) { s->done = 1; s->breakdown = 1; }       // Krylov.jl stops on non-positive curvature
 }
-__device__ __forceinline__ void cg_after_gamma(CGScalars* s, double gnew, double* hist, i64 hist_cap) {
+// gnew = r'Mr of the new residual; res2 = square of the residual norm the stopping test uses (= gnew for Krylov.jl's M-norm rule,
+// r'r for the plain l2 rule)
+__device__ __forceinline__ void cg_after_gamma(CGScalars* s, double gnew, double* hist, i64 hist_cap, double res2 = -1.0) {
     s->beta = gnew / s->gamma;
     s->gamma = gnew;
     s->iter += 1;
-    double res = sqrt(gnew);
+    double res = sqrt(res2 >= 0.0 ? res2 : gnew);
+    s->res = res;
     if (s->iter < hist_cap) hist[s->iter] = res;
     if (res <= s->eps) { s->done = 1; s->converged = 1; }
     else if (s->iter >= s->itmax) s->done = 1;

@@ -76,7 +76,6 @@ struct DistState {
     DevBuf<int> send_nodes;               // n_shared_total: local node id per send slot
     DevBuf<double> sendbuf, recvbuf;      // 2 x 3 * n_shared_total: staging alternates between two halves from one exchange to the next
     int xpar = 0;
-    bool warmed = false;                  // the communicator has carried a burst of exchange traffic (see dist_warm_up)
     DevBuf<int> if_node, if_ptr, if_src;  // unpack CSR: for interface node i, sources in ascending rank order; src = -1 → own value, else recv slot
     DevBuf<double> gvec;                  // global-length scratch for gathers
     // peer-memory exchange (CUDA IPC over NVLink/NVSwitch): one kernel does pack + interface sum + scalar allreduce
@@ -90,7 +89,7 @@ struct DistState {
     u64 xseq = 0;                         // exchange sequence number (identical on all ranks)
     DevBuf<u64> gbar;                     // grid-barrier counter of the exchange kernel (monotonic)
     u64 xlaunch = 0;                      // launches of the exchange kernel so far (local)
-    // all-gather exchange (opt-in, TOE_DIST_XCHG=allgather): ONE collective per operator application carries every rank's packed
+    // all-gather exchange (default transport): ONE collective per operator application carries every rank's packed
     // interface values plus its two partial scalars; each rank picks its neighbours' segments out of the gathered buffer
     bool ag_ok = false;
     i64 ag_stride = 0;                    // doubles per rank in the gathered buffer: 3 * max_r(n_shared_total) + 2 (even → 16-byte slices)
@@ -103,6 +102,21 @@ static int allgather_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& i
 static int exchange_allgather(toe_ctx* ctx, double* y, double* scal, int count);
 
 bool dist_active(toe_ctx* ctx) { return ctx->dist != nullptr; }
+
+// Transport of the per-iteration exchange (read at every set-up):
+//   allgather (default)  ONE ncclAllGather carries every rank's packed interface values and its partial scalars
+//   sendrecv             grouped ncclSend/ncclRecv per neighbour + ncclAllReduce of the scalars.  NOT the default: at 10M tets / N=2 on this
+//                        stack (NCCL 2.28.9, B200, one process per GPU) roughly one solve in ten met a transient fault in mid-iteration
+//                        (identical state fingerprints before the solve, residual history leaving the reference run at iteration ~7500,
+//                        bit-identical on both ranks; 3 of 29 solves, against 0 of 36 on the two other transports — profiles/r2_dist_diagnosis.md)
+//   p2p                  fused peer-memory kernel over CUDA IPC mailboxes (also TOE_DIST_P2P=1)
+enum XchgMode { XCHG_ALLGATHER = 0, XCHG_SENDRECV = 1, XCHG_P2P = 2 };
+static XchgMode xchg_mode() {
+    const char* m = getenv("TOE_DIST_XCHG");
+    if (m && strcmp(m, "sendrecv") == 0) return XCHG_SENDRECV;
+    if ((m && strcmp(m, "p2p") == 0) || (!m && getenv("TOE_DIST_P2P"))) return XCHG_P2P;
+    return XCHG_ALLGATHER;
+}
 
 static void mailbox_close_peers(DistState* d) {
     for (int r = 0; r < (int)d->peer_mbox.size(); r++)
@@ -150,8 +164,6 @@ int dist_comm_init(toe_ctx* ctx, int nranks, int rank, const char id[128]) {
     ctx->dist = d;
     return TOE_OK;
 }
-
-static int dist_warm_up(toe_ctx* ctx);
 
 int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count) {
     if (!ctx->dist || ctx->dist->nranks == 1) return TOE_OK;
@@ -430,7 +442,6 @@ int dist_set_mesh(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, cons
     CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
     TRY(mailbox_setup(ctx, d, if_src));
     TRY(allgather_setup(ctx, d, if_src));
-    TRY(dist_warm_up(ctx));
     return dist_align(ctx);
 }
 
@@ -452,25 +463,6 @@ __global__ void k_unpack_sum(const int* __restrict__ if_node, const int* __restr
     double own = y[dof], s = 0.0;
     for (int j = if_ptr[k]; j < if_ptr[k + 1]; j++) { int src = if_src[j]; s += src < 0 ? own : recv[3 * (size_t)src + c]; }   // ascending rank order
     y[dof] = s;
-}
-
-// First-use traffic: NCCL establishes p2p / collective connections lazily, and the very first PCG solve on a fresh communicator
-// was seen to break down once at 10M tets (N=2) while identical later solves converged.  A burst of the exact per-iteration
-// pattern (halo send/recv + 2-double allreduce) on scratch data right after the first partitioned set-up keeps that phase out
-// of real solves; the restart logic in solve_pcg remains as the safety net.
-static int dist_warm_up(toe_ctx* ctx) {
-    DistState* d = ctx->dist;
-    if (!d || d->nranks == 1 || d->warmed || !getenv("TOE_DIST_WARMUP")) return TOE_OK;      // opt-in (A/B diagnostic); off by default
-    size_t n = 3 * (size_t)ctx->nq;
-    DevBuf<double> scratch; CU(scratch.alloc(n + 2));
-    CU(cudaMemsetAsync(scratch.p, 0, (n + 2) * sizeof(double), ctx->stream));
-    for (int it = 0; it < 2000; it++) {
-        TRY(dist_post_spmv(ctx, scratch.p));
-        NC(g_nccl.AllReduce(scratch.p + n, scratch.p + n, 2, ncclDouble, ncclSum, d->comm, ctx->stream));
-    }
-    CU(cudaStreamSynchronize(ctx->stream));
-    d->warmed = true;
-    return TOE_OK;
 }
 
 int dist_post_spmv(toe_ctx* ctx, double* y) {
@@ -613,9 +605,8 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_xchg(char* const* __restrict__
 // (re)creates the mailboxes and exchanges their IPC handles; collective.  Falls back to the NCCL path on any failure.
 static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host) {
     d->p2p_ok = false;
-    // opt-in (TOE_DIST_P2P=1): measured 9 % faster than the NCCL group at N=8, but one 4-GPU run at 10M tets timed out in
-    // the flag wait (cause not yet found), so the NCCL transport stays the default until that is understood
-    if (d->nranks == 1 || !getenv("TOE_DIST_P2P") || getenv("TOE_DIST_NO_P2P")) return TOE_OK;
+    // opt-in (TOE_DIST_XCHG=p2p): one 4-GPU run at 10M tets timed out in the flag wait in round 1 (cause not found)
+    if (d->nranks == 1 || xchg_mode() != XCHG_P2P) return TOE_OK;
     // agree on the receive-area stride
     int my_max = 1;
     for (int c : d->nbr_count) my_max = std::max(my_max, c);
@@ -698,26 +689,27 @@ static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// All-gather exchange (opt-in: TOE_DIST_XCHG=allgather).  Interfaces are small (157 KB per neighbour at 10M tets / N=2), so
+// All-gather exchange (the default transport).  Interfaces are small (157 KB per neighbour at 10M tets / N=2), so
 // instead of a group of sends / receives plus an allreduce every rank contributes ONE slice — its packed interface values in
 // its own send layout, then its two partial scalars — to ONE ncclAllGather; the unpack kernel reads the neighbours' segments
 // straight out of the gathered buffer (offsets exchanged once per set-up) and sums the scalars in rank order.  Same arithmetic
 // and summation order as the other transports → bit-identical iterates.  3 launches per exchange instead of 4, and no
 // point-to-point traffic at all.
 // ---------------------------------------------------------------------------------------------------------
+static const int AG_SCALARS = 4;       // scalar slots at the end of every rank's slice ({γ, δ, ν, spare})
 __global__ void k_pack_ag(const int* __restrict__ send_nodes, const double* __restrict__ y, const double* scal, int nscal,
                           double* __restrict__ slice, int n, i64 stride) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 3 * n) { int s = i / 3, c = i - 3 * s; slice[i] = y[3 * (size_t)send_nodes[s] + c]; }
-    if (i < 2) slice[stride - 2 + i] = (i < nscal) ? scal[i] : 0.0;
+    if (i < AG_SCALARS) slice[stride - AG_SCALARS + i] = (i < nscal) ? scal[i] : 0.0;
 }
 __global__ void k_unpack_ag(const int* __restrict__ if_node, const int* __restrict__ if_ptr, const int* __restrict__ if_src_ag,
                             const double* __restrict__ all, double* __restrict__ y, int n_if, double* scal, int nscal, int nranks, i64 stride) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && nscal > 0) {                                   // scalars in rank order: identical bits on every rank
-        double s0 = 0.0, s1 = 0.0;
-        for (int r = 0; r < nranks; r++) { s0 += all[(size_t)r * stride + stride - 2]; s1 += all[(size_t)r * stride + stride - 1]; }
-        scal[0] = s0; if (nscal > 1) scal[1] = s1;
+    if (i < nscal) {                                             // scalars in rank order: identical bits on every rank
+        double s = 0.0;
+        for (int r = 0; r < nranks; r++) s += all[(size_t)r * stride + stride - AG_SCALARS + i];
+        scal[i] = s;
     }
     if (i >= 3 * n_if) return;
     int k = i / 3, c = i - 3 * k;
@@ -730,8 +722,7 @@ __global__ void k_unpack_ag(const int* __restrict__ if_node, const int* __restri
 // collective; called at every set-up.  Publishes, for every (rank r, peer q), where r's segment for q starts in r's send layout.
 static int allgather_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host) {
     d->ag_ok = false;
-    const char* mode = getenv("TOE_DIST_XCHG");
-    if (d->nranks == 1 || !mode || strcmp(mode, "allgather") != 0 || d->p2p_ok) return TOE_OK;
+    if (d->nranks == 1 || xchg_mode() != XCHG_ALLGATHER || d->p2p_ok) return TOE_OK;
     const int R = d->nranks;
     std::vector<int> tab((size_t)R * R + 1, 0);                  // own row: 1 + offset of the segment for peer q (0 = not a neighbour); last: max n_shared_total
     for (size_t k = 0; k < d->nbr.size(); k++) tab[(size_t)d->rank * R + d->nbr[k]] = 1 + d->nbr_off[k];
@@ -745,9 +736,9 @@ static int allgather_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& i
     CU(cudaMemcpyAsync(tab.data(), dt.p, (size_t)R * R * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(&gmax, dm.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    // per-rank slice: 3 * max_r(n_shared_total) interface doubles + 2 scalars, rounded up to a multiple of 6 doubles so that slices
+    // per-rank slice: 3 * max_r(n_shared_total) interface doubles + AG_SCALARS scalars, rounded up to a multiple of 6 doubles so that slices
     // are 16-byte aligned AND start on a node slot (a source is then addressed by ONE int: node slot in the gathered buffer)
-    d->ag_stride = (3 * (i64)gmax + 2 + 5) / 6 * 6;
+    d->ag_stride = (3 * (i64)gmax + AG_SCALARS + 5) / 6 * 6;
     const i64 slots_per_rank = d->ag_stride / 3;
     if ((i64)R * slots_per_rank > 2147483647LL / 4) return TOE_OK;        // would not fit the int indices: stay on send/recv
     // source of my recv slot p (segment k of MY layout, position j) = slice of rank nbr[k], its segment for me, position j
@@ -778,10 +769,10 @@ static int exchange_allgather(toe_ctx* ctx, double* y, double* scal, int count) 
     d->xpar ^= 1;
     double* slice = d->ag_send.p + (size_t)d->xpar * d->ag_stride;
     double* all = d->ag_recv.p + (size_t)d->xpar * d->nranks * d->ag_stride;
-    const i64 work = std::max<i64>(3 * (i64)n, 2);
+    const i64 work = std::max<i64>(3 * (i64)n, AG_SCALARS);
     LAUNCH(ctx, k_pack_ag, div_up(work, 256), 256, 0, (const int*)d->send_nodes.p, (const double*)y, (const double*)scal, count, slice, n, d->ag_stride);
     NC(g_nccl.AllGather(slice, all, (size_t)d->ag_stride, ncclDouble, d->comm, ctx->stream));
-    const i64 work2 = std::max<i64>(3 * (i64)d->n_if, 1);
+    const i64 work2 = std::max<i64>(3 * (i64)d->n_if, AG_SCALARS);
     LAUNCH(ctx, k_unpack_ag, div_up(work2, 256), 256, 0, (const int*)d->if_node.p, (const int*)d->if_ptr.p, (const int*)d->if_src_ag.p,
            (const double*)all, y, d->n_if, scal, count, d->nranks, d->ag_stride);
     return TOE_OK;
@@ -802,7 +793,7 @@ int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count) {
                &ctx->cgs.p->done, ctx->errflag.p + 2, d->gbar.p, d->xlaunch++);
         return TOE_OK;
     }
-    if (d->ag_ok && count <= 2) return exchange_allgather(ctx, y, scal, count);
+    if (d->ag_ok && count <= AG_SCALARS) return exchange_allgather(ctx, y, scal, count);
     int n = d->n_shared_total;
     d->xpar ^= 1;
     double* sb = d->sendbuf.p + (size_t)d->xpar * 3 * n;

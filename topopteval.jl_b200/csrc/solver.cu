@@ -345,26 +345,29 @@ static const int VEC_THREADS = 256;
 static unsigned vec_grid(size_t n) { return min_u(div_up((i64)n, VEC_THREADS), (unsigned)(N_SM * 8)); }
 
 // x = 0, r = f, Minv = 1 ./ D with D[abs(D) < 1e-12] = 1 (RobustSolver.jl:231-236), z = M r, p = z, γ = r'z
+// L2: the stopping test uses ‖r‖₂ instead of Krylov.jl's √(r'Mr) (TOE_PCG_L2_NORM)
+template <bool L2>
 __global__ void __launch_bounds__(VEC_THREADS) k_cg_init(const double* __restrict__ f, const double* __restrict__ diag, double* __restrict__ Minv,
                                                          double* __restrict__ x, double* __restrict__ r, double* __restrict__ p, size_t n,
                                                          CGScalars* cg, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap,
-                                                         double* partials, unsigned int* counter,
-                                                         const unsigned char* __restrict__ owned, double* local_out) {
+                                                         double* partials, unsigned int* counter) {
     __shared__ double red[32];
-    double s = 0.0;
+    double s = 0.0, s2 = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double d = diag[i];
         if (fabs(d) < 1e-12) d = 1.0;
         double mi = 1.0 / d, ri = f[i], zi = mi * ri;
         Minv[i] = mi; x[i] = 0.0; r[i] = ri; p[i] = zi;
-        if (!owned || owned[i / 3]) s += ri * zi;
+        s += ri * zi;
+        if (L2) s2 += ri * ri;
     }
     s = block_sum(s, red);
-    double tot;
-    if (grid_sum_last_block(s, partials, counter, red, &tot)) {
-        if (local_out) { *local_out = tot; return; }       // caller closes the recurrence itself
+    if (L2) s2 = block_sum(s2, red);
+    double tot, tot2 = 0.0;
+    if (L2 ? grid_sum2_last_block(s, s2, partials, counter, red, &tot, &tot2) : grid_sum_last_block(s, partials, counter, red, &tot)) {
         cg->gamma = tot; cg->pAp = 0.0; cg->beta = 0.0;
-        cg->res0 = sqrt(tot);
+        cg->res0 = sqrt(L2 ? tot2 : tot);
+        cg->res = cg->res0;
         cg->eps = atol + rtol * cg->res0;
         cg->iter = 0; cg->itmax = itmax;
         cg->converged = (cg->res0 <= cg->eps) ? 1 : 0;
@@ -375,26 +378,27 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_init(const double* __restric
 }
 
 // α = γ/p'Ap, x += α p, r -= α Ap, γ' = r' M r; the last block closes the iteration (β, convergence test)
+template <bool L2>
 __global__ void __launch_bounds__(VEC_THREADS) k_cg_xr(const double* __restrict__ p, const double* __restrict__ Ap, const double* __restrict__ Minv,
                                                        double* __restrict__ x, double* __restrict__ r, size_t n, CGScalars* cg,
-                                                       double* hist, i64 hist_cap, double* partials, unsigned int* counter,
-                                                       const unsigned char* __restrict__ owned, double* local_out) {
+                                                       double* hist, i64 hist_cap, double* partials, unsigned int* counter) {
     __shared__ double red[32];
     if (cg->done) return;
     const double alpha = cg->gamma / cg->pAp;
-    double s = 0.0;
+    double s = 0.0, s2 = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double pi = p[i];
         x[i] += alpha * pi;
         double ri = r[i] - alpha * Ap[i];
         r[i] = ri;
-        if (!owned || owned[i / 3]) s += ri * ri * Minv[i];
+        s += ri * ri * Minv[i];
+        if (L2) s2 += ri * ri;
     }
     s = block_sum(s, red);
-    double tot;
-    if (grid_sum_last_block(s, partials, counter, red, &tot)) {
-        if (local_out) *local_out = tot; else cg_after_gamma(cg, tot, hist, hist_cap);
-    }
+    if (L2) s2 = block_sum(s2, red);
+    double tot, tot2 = -1.0;
+    if (L2 ? grid_sum2_last_block(s, s2, partials, counter, red, &tot, &tot2) : grid_sum_last_block(s, partials, counter, red, &tot))
+        cg_after_gamma(cg, tot, hist, hist_cap, tot2);
 }
 
 // p = M r + β p
@@ -459,10 +463,10 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_init(const double* __restr
         Minv[i] = mi; x[i] = 0.0; r[i] = ri; z[i] = mi * ri; p[i] = 0.0; s[i] = 0.0;
     }
 }
-__global__ void k_cgcg_fin_init(CGScalars* cg, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap) {
+__global__ void k_cgcg_fin_init(CGScalars* cg, double atol, double rtol, i64 itmax, double* hist, i64 hist_cap, int l2) {
     if (threadIdx.x || blockIdx.x) return;
     double g = cg->gd[0][0];
-    cg->gamma = g; cg->res0 = sqrt(g); cg->eps = atol + rtol * cg->res0;
+    cg->gamma = g; cg->res0 = sqrt(l2 ? cg->gd[0][2] : g); cg->res = cg->res0; cg->eps = atol + rtol * cg->res0;
     cg->iter = 0; cg->itmax = itmax; cg->breakdown = 0; cg->beta = 0.0; cg->pAp = 0.0;
     cg->converged = 0; cg->done = 0;
     cg->alpha[0] = cg->alpha[1] = 1.0;
@@ -471,21 +475,21 @@ __global__ void k_cgcg_fin_init(CGScalars* cg, double atol, double rtol, i64 itm
 __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restrict__ Minv, const double* __restrict__ w, double* __restrict__ z,
                                                           double* __restrict__ p, double* __restrict__ s, double* __restrict__ x, double* __restrict__ r,
                                                           size_t n, CGScalars* cg, int par, double* hist, i64 hist_cap,
-                                                          const unsigned char* __restrict__ owned, double* partials, unsigned int* counter) {
+                                                          const unsigned char* __restrict__ owned, double* partials, unsigned int* counter, int l2) {
     __shared__ double red[32];
     if (cg->done) return;
     const i64 j = cg->iter;                        // advanced once, by the last block of this launch, after every block has read it
     const double g = cg->gd[par][0], dl = cg->gd[par][1];
     const double gprev = cg->gd[par ^ 1][0], aprev = cg->alpha[par ^ 1];
     const bool first = (j == 0);
-    const double res = sqrt(g);
+    const double res = sqrt(l2 ? cg->gd[par][2] : g);
     const bool conv = res <= cg->eps, tired = j >= cg->itmax;
     const double beta = first ? 0.0 : g / gprev;
     const double denom = first ? dl : dl - beta * g / aprev;       // = p'Ap in exact arithmetic
     const bool brk = !(denom > 0.0) && !conv && !tired;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (j < hist_cap) hist[j] = res;
-        cg->gamma = g;
+        cg->gamma = g; cg->res = res;
         if (conv) { cg->converged = 1; cg->done = 1; }
         else if (tired) cg->done = 1;
         else if (brk) { cg->breakdown = 1; cg->done = 1; }
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restri
     }
     if (conv || tired || brk) return;
     const double alpha = g / denom;
-    double gs = 0.0;
+    double gs = 0.0, ns = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         double pi = z[i] + beta * p[i];
         double si = w[i] + beta * s[i];
@@ -503,12 +507,13 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restri
         r[i] = ri;
         double zi = Minv[i] * ri;
         z[i] = zi;
-        if (!owned || owned[i / 3]) gs += ri * zi;
+        if (!owned || owned[i / 3]) { gs += ri * zi; ns += ri * ri; }
     }
-    // γ_{j+1} = r'Mr over owned dofs: local partial into the other parity slot (allreduced after the operator)
+    // γ_{j+1} = r'Mr (and ν_{j+1} = r'r) over owned dofs: local partials into the other parity slot (summed over the ranks after the operator)
     gs = block_sum(gs, red);
-    double tot;
-    if (grid_sum_last_block(gs, partials, counter, red, &tot)) { cg->gd[par ^ 1][0] = tot; cg->iter = j + 1; }
+    ns = block_sum(ns, red);
+    double tot, tot2;
+    if (grid_sum2_last_block(gs, ns, partials, counter, red, &tot, &tot2)) { cg->gd[par ^ 1][0] = tot; cg->gd[par ^ 1][2] = tot2; cg->iter = j + 1; }
 }
 int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count);
 int dist_check_exchange(toe_ctx* ctx);     // dist.cu: interface sum of y + allreduce of scal in ONE NCCL group
@@ -516,17 +521,17 @@ int dist_check_exchange(toe_ctx* ctx);     // dist.cu: interface sum of y + allr
 // one iteration of the partitioned single-reduction CG; `par` = iteration parity (baked into captured graphs).
 // 4 kernels + one NCCL group: the δ partial is the operator's own fused dot over ALL local rows (Σ_ranks w_local·z equals
 // w·z because z is interface-consistent), so the allreduce does not have to wait for the interface sum.
-static int cgcg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, int par) {
+static int cgcg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, int par, int l2) {
     CGScalars* cg = ctx->cgs.p;
     double* z = ctx->cg_z.p; double* w = ctx->Ap.p;
     LAUNCH(ctx, k_cgcg_vec, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->Minv.p, (const double*)w, z, ctx->p.p, ctx->cg_s.p, ctx->u.p, ctx->r.p,
-           n, cg, par, ctx->hist.p, hist_cap, ctx->owned, ctx->partials.p, ctx->counters.p + 8);
+           n, cg, par, ctx->hist.p, hist_cap, ctx->owned, ctx->partials.p, ctx->counters.p + 8, l2);
     TRY(op_launch(ctx, z, w, matrix_free, cg, true, &cg->done, &cg->gd[par ^ 1][1]));
-    TRY(dist_exchange_allreduce(ctx, w, &cg->gd[par ^ 1][0], 2));
+    TRY(dist_exchange_allreduce(ctx, w, &cg->gd[par ^ 1][0], l2 ? 3 : 2));
     return TOE_OK;
 }
 
-static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, bool two_level = false) {
+static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, bool two_level = false, int l2 = 0) {
     CGScalars* cg = ctx->cgs.p;
     if (two_level) {
         if (ctx->dist) {     // partitioned: the local p'Ap partial (all local rows: p is interface-consistent) rides with the interface sum
@@ -539,8 +544,10 @@ static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, b
     }
     {
         TRY(op_launch(ctx, ctx->p.p, ctx->Ap.p, matrix_free, cg, true));
-        LAUNCH(ctx, k_cg_xr, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p,
-               ctx->u.p, ctx->r.p, n, cg, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p + 2, (const unsigned char*)nullptr, (double*)nullptr);
+#define XR_ARGS (const double*)ctx->p.p, (const double*)ctx->Ap.p, (const double*)ctx->Minv.p, ctx->u.p, ctx->r.p, n, cg, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p + 2
+        if (l2) LAUNCH(ctx, k_cg_xr<true>, vec_grid(n), VEC_THREADS, 0, XR_ARGS);
+        else    LAUNCH(ctx, k_cg_xr<false>, vec_grid(n), VEC_THREADS, 0, XR_ARGS);
+#undef XR_ARGS
     }
     LAUNCH(ctx, k_cg_p, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->Minv.p, ctx->p.p, n, (const CGScalars*)cg);
     return TOE_OK;
@@ -549,21 +556,39 @@ static int cg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap, b
 static const int CG_BATCH_DEFAULT = 50;       // iterations per host check / captured graph (always even: parity-indexed scalars)
 static const i64 HIST_CAP = 1LL << 20;
 
+// Σ_owned w_i (a_i - b_i)^2  (w = null: plain sum of squares)
+__global__ void __launch_bounds__(VEC_THREADS) k_wdiff2(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ w, size_t n,
+                                                        const unsigned char* __restrict__ owned, double* partials, unsigned int* counter, double* out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (owned && !owned[i / 3]) continue;
+        double d = a[i] - b[i];
+        s += (w ? w[i] : 1.0) * d * d;
+    }
+    s = block_sum(s, red);
+    double tot;
+    if (grid_sum_last_block(s, partials, counter, red, &tot)) *out = tot;
+}
+
 int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap) {
     int matrix_free = (flags & TOE_PCG_MATRIX_FREE) ? 1 : 0;
+    const int l2 = (flags & TOE_PCG_L2_NORM) ? 1 : 0;
     if (!matrix_free && !ctx->have_K) return toe_fail(ctx, TOE_ERR_STATE, "solve: K is not assembled (or pass TOE_PCG_MATRIX_FREE)");
     if (matrix_free && ctx->mat.mode == MAT_NONE) return toe_fail(ctx, TOE_ERR_STATE, "solve: no material set");
     if (itmax < 0) return toe_fail(ctx, TOE_ERR_ARG, "solve: itmax must be >= 0");
+    const bool dist = ctx->dist != nullptr;
+    const bool two_level = (flags & TOE_PCG_TWO_LEVEL) != 0;
+    if (l2 && two_level) return toe_fail(ctx, TOE_ERR_ARG, "solve: TOE_PCG_L2_NORM is implemented for the Jacobi preconditioner only");
     TRY(ensure_vectors(ctx));
     TRY(compute_diag(ctx));
     if (matrix_free && !getenv("TOE_EBE_GATHER")) TRY(mesh_build_tiles(ctx));     // allocations must not happen inside graph capture
     size_t n = 3 * (size_t)ctx->nq;
     const i64 hist_cap = HIST_CAP;            // fixed: pointer and capacity are baked into the captured graph
     CU(ctx->hist.alloc(hist_cap));
+    if (dist) { CU(ctx->cg_s.alloc(n)); CU(ctx->cg_z.alloc(n)); }
     if (!ctx->cgs_host) CU(cudaMallocHost((void**)&ctx->cgs_host, sizeof(CGScalars)));
     i64 launches0 = ctx->launches;
-    const bool dist = ctx->dist != nullptr;
-    const bool two_level = (flags & TOE_PCG_TWO_LEVEL) != 0;
     const int per_iter = two_level ? 6 : (dist ? 4 : 3);
     int coarse_dofs = 0; double precond_seconds = 0.0;
     int CG_BATCH = CG_BATCH_DEFAULT;
@@ -574,61 +599,56 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     cudaEvent_t e0 = ev.a, e1 = ev.b;
     CU(cudaEventRecord(e0, ctx->stream));
     if (two_level) TRY(tl_prepare(ctx, matrix_free, &coarse_dofs, &precond_seconds));      // ZᵀKZ and its inverse: part of the solve time
-    // Partitioned runs: a solve that ends in a CG breakdown is restarted from x0 = 0 (at most twice) and the number of restarts is
-    // reported.  One such first solve was seen at N=2 / 10M tets on the NCCL transport (identical re-runs converge); the restart
-    // keeps the result valid while the cause is open.  TOE_DIST_NO_RETRY=1 disables it.
-    int restarts = 0;
-    for (;; restarts++) {
-        if (restarts > 0) {                        // a restart recomputes the Jacobi diagonal too (its interface sum is an exchange)
-            ctx->have_diag = false;
-            TRY(compute_diag(ctx));
-        }
-        if (two_level) {
-            TRY(tl_cg_init(ctx, atol, rtol, itmax, hist_cap));
-        } else if (!dist) {
-            LAUNCH(ctx, k_cg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n,
-                   ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p, (const unsigned char*)nullptr, (double*)nullptr);
-        } else {
-            CU(ctx->cg_s.alloc(n)); CU(ctx->cg_z.alloc(n));
-            CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
-            CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
-            LAUNCH(ctx, k_cgcg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->cg_z.p,
-                   ctx->p.p, ctx->cg_s.p, n);
-            LAUNCH(ctx, k_dot_masked, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->cg_z.p, n, ctx->owned, (const int*)nullptr,
-                   ctx->partials.p, ctx->counters.p + 8, &ctx->cgs.p->gd[0][0]);
-            TRY(op_launch(ctx, ctx->cg_z.p, ctx->Ap.p, matrix_free, ctx->cgs.p, true, &ctx->cgs.p->done, &ctx->cgs.p->gd[0][1]));
-            TRY(dist_exchange_allreduce(ctx, ctx->Ap.p, &ctx->cgs.p->gd[0][0], 2));
-            LAUNCH(ctx, k_cgcg_fin_init, 1, 32, 0, ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap);
-        }
+    if (two_level) {
+        TRY(tl_cg_init(ctx, atol, rtol, itmax, hist_cap));
+    } else if (!dist) {
+#define INIT_ARGS (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->p.p, n, ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, ctx->partials.p, ctx->counters.p
+        if (l2) LAUNCH(ctx, k_cg_init<true>, vec_grid(n), VEC_THREADS, 0, INIT_ARGS);
+        else    LAUNCH(ctx, k_cg_init<false>, vec_grid(n), VEC_THREADS, 0, INIT_ARGS);
+#undef INIT_ARGS
+    } else {
+        CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
+        CU(cudaMemsetAsync(ctx->cgs.p, 0, sizeof(CGScalars), ctx->stream));
+        LAUNCH(ctx, k_cgcg_init, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->diag.p, ctx->Minv.p, ctx->u.p, ctx->r.p, ctx->cg_z.p,
+               ctx->p.p, ctx->cg_s.p, n);
+        LAUNCH(ctx, k_dot_masked, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->cg_z.p, n, ctx->owned, (const int*)nullptr,
+               ctx->partials.p, ctx->counters.p + 8, &ctx->cgs.p->gd[0][0]);
+        if (l2) LAUNCH(ctx, k_dot_masked, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->r.p, (const double*)ctx->r.p, n, ctx->owned, (const int*)nullptr,
+                       ctx->partials.p, ctx->counters.p + 8, &ctx->cgs.p->gd[0][2]);
+        TRY(op_launch(ctx, ctx->cg_z.p, ctx->Ap.p, matrix_free, ctx->cgs.p, true, &ctx->cgs.p->done, &ctx->cgs.p->gd[0][1]));
+        TRY(dist_exchange_allreduce(ctx, ctx->Ap.p, &ctx->cgs.p->gd[0][0], l2 ? 3 : 2));
+        LAUNCH(ctx, k_cgcg_fin_init, 1, 32, 0, ctx->cgs.p, atol, rtol, itmax, ctx->hist.p, hist_cap, l2);
+    }
 
-        bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
-        if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture stalled on this stack; direct launches for now
-        i64 key = (ctx->op_generation * 8 + (two_level ? 4 : 0) + matrix_free * 2 + 1) * 4096 + CG_BATCH;
-        if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
-            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
-            cudaGraph_t g = nullptr;
-            CU(cudaStreamBeginCapture(ctx->stream, dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
-            i64 l0 = ctx->launches;
-            int st = TOE_OK;
-            for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = (dist && !two_level) ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level);
-            ctx->launches = l0;
-            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
-            if (st != TOE_OK) { if (g) cudaGraphDestroy(g); return st; }
-            if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
-            cudaGraphDestroy(g);
-            if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-            ctx->graph_key = key;
-        }
-        i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
-        for (i64 bt = 0; bt < max_batches; bt++) {
-            if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += per_iter * CG_BATCH; }
-            else for (int k = 0; k < CG_BATCH; k++) TRY((dist && !two_level) ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level));
-            CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            if (ctx->cgs_host->done) break;
-        }
-        if (!dist || !ctx->cgs_host->breakdown || restarts >= 2 || getenv("TOE_DIST_NO_RETRY")) break;
+    auto one_iteration = [&](int k) -> int {
+        return (dist && !two_level) ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1, l2) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level, l2);
+    };
+    bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
+    if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture: opt-in (TOE_DIST_GRAPH=1) until measured
+    i64 key = ((ctx->op_generation * 2 + l2) * 8 + (two_level ? 4 : 0) + matrix_free * 2 + 1) * 4096 + CG_BATCH;
+    if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
+        if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(ctx->stream, dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
+        i64 l0 = ctx->launches;
+        int st = TOE_OK;
+        for (int k = 0; k < CG_BATCH && st == TOE_OK; k++) st = one_iteration(k);
+        ctx->launches = l0;
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        if (st != TOE_OK) { if (g) cudaGraphDestroy(g); return st; }
+        if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return toe_fail(ctx, TOE_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        ctx->graph_key = key;
+    }
+    i64 max_batches = (itmax + CG_BATCH - 1) / CG_BATCH + 1;
+    for (i64 bt = 0; bt < max_batches; bt++) {
+        if (use_graph) { CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream)); ctx->launches += per_iter * CG_BATCH; }
+        else for (int k = 0; k < CG_BATCH; k++) TRY(one_iteration(k));
+        CU(cudaMemcpyAsync(ctx->cgs_host, ctx->cgs.p, sizeof(CGScalars), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->cgs_host->done) break;
     }
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaEventSynchronize(e1));
@@ -639,20 +659,28 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     if (dist) TRY(dist_check_exchange(ctx));
     ctx->have_solution = true;
 
+    // true residual f - K u, in the l2 norm (RobustSolver.jl:468) and in the norm of the stopping test.  A converged recurrence whose true
+    // residual is orders of magnitude away means the iterates were corrupted on the way (a faulty exchange cannot make p'Ap <= 0 by
+    // itself): that is an error, never a result.
+    TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
+    TRY(dist_post_spmv(ctx, ctx->tmp.p));
+    double* out = ctx->partials.p + 3 * (N_SM * 8) + 8;
+    LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->tmp.p, n, out, ctx->partials.p, ctx->counters.p + 4, ctx->owned);
+    LAUNCH(ctx, k_wdiff2, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->tmp.p, (const double*)(two_level ? nullptr : ctx->Minv.p), n,
+           ctx->owned, ctx->partials.p, ctx->counters.p + 7, out + 3);
+    TRY(dist_allreduce(ctx, out, 4));
+    double hn[4];
+    CU(cudaMemcpyAsync(hn, out, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const double rel_res_l2 = hn[1] > 0 ? sqrt(hn[0] / hn[1]) : sqrt(hn[0]);
+    const double true_res = (l2 || two_level) ? sqrt(hn[0]) : sqrt(hn[3]);
+    const double final_res = two_level ? sqrt(h.gamma) : h.res;
     if (stats) {
         stats->niter = h.iter; stats->converged = h.converged; stats->breakdown = h.breakdown;
-        stats->res0_M = h.res0; stats->res_M = sqrt(h.gamma);
+        stats->res0_M = h.res0; stats->res_M = final_res;
         stats->solve_seconds = ms * 1e-3;
-        // true residual ||f - K u|| / ||f||  (RobustSolver.jl:468)
-        TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, true));
-        TRY(dist_post_spmv(ctx, ctx->tmp.p));
-        double* out = ctx->partials.p + 3 * (N_SM * 8) + 8;
-        LAUNCH(ctx, k_norms, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->f.p, (const double*)ctx->tmp.p, n, out, ctx->partials.p, ctx->counters.p + 4, ctx->owned);
-        TRY(dist_allreduce(ctx, out, 3));
-        double hn[3];
-        CU(cudaMemcpyAsync(hn, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        stats->rel_res_l2 = hn[1] > 0 ? sqrt(hn[0] / hn[1]) : sqrt(hn[0]);
+        stats->rel_res_l2 = rel_res_l2;
+        stats->true_res = true_res;
         // operator time: a few isolated launches (local product only)
         const int reps = 5;
         EventPair ev2; CU(ev2.create());
@@ -666,7 +694,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         stats->spmv_seconds = (double)h.iter * (oms * 1e-3 / reps);
         stats->spmv_bytes = op_bytes(ctx, matrix_free);
         stats->kernel_launches = ctx->launches - launches0;
-        stats->restarts = restarts;
+        stats->restarts = 0;
         stats->coarse_dofs = coarse_dofs; stats->precond_seconds = precond_seconds;
     }
     if (history && history_cap > 0) {
@@ -674,6 +702,9 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         if (cnt > hist_cap) cnt = hist_cap;
         CU(cudaMemcpy(history, ctx->hist.p, cnt * sizeof(double), cudaMemcpyDeviceToHost));
     }
+    if (h.converged && !two_level && !(true_res <= 1e4 * fmax(h.eps, final_res)))
+        return toe_fail(ctx, TOE_ERR_NUMERIC, "solve: the recurrence reports convergence (residual %.3e <= %.3e after %lld iterations) but the true residual "
+                        "of the returned u is %.3e in the same norm: the iterates were corrupted", final_res, h.eps, (long long)h.iter, true_res);
     return TOE_OK;
 }
 

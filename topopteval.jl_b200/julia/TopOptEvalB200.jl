@@ -230,7 +230,7 @@ struct PcgStats
     niter::Int64; converged::Int32; breakdown::Int32
     res0_M::Float64; res_M::Float64; rel_res_l2::Float64
     solve_seconds::Float64; spmv_seconds::Float64; spmv_bytes::Float64; kernel_launches::Int64; restarts::Int64
-    coarse_dofs::Int64; precond_seconds::Float64
+    coarse_dofs::Int64; precond_seconds::Float64; true_res::Float64
 end
 
 "Lazy stand-in for Dict{Int,Vector{SymmetricTensor}}: nothing leaves the GPU until indexed (`fetch!` fills a 6 × nqp × ne array)."
