@@ -198,6 +198,10 @@ int toe_spmv(toe_ctx* ctx, const double* x, double* y, int matrix_free);
 /* times `reps` back-to-back operator applications on device vectors; returns average seconds and the
  * algorithmic bytes of one application. */
 int toe_time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out);
+/* diagnostic: applies the operator to the stored vector u `reps`+1 times (on a partitioned ctx: local product + interface sum) and
+ * compares every result bit for bit with the first on the device.  The path is deterministic, so both counts must be 0:
+ * mismatching_batches = batches of 256 applications in which a difference appeared, mismatching_entries = differing entries in total. */
+int toe_spmv_soak(toe_ctx* ctx, int matrix_free, int64_t reps, int64_t* mismatching_batches, int64_t* mismatching_entries);
 
 /* ---- multi-GPU: one ctx per GPU / process, element-based domain decomposition --------------------------- */
 /* NCCL (dlopen'ed libnccl.so.2) send/recv for the interface-DOF exchange and allreduce for the CG scalars.

@@ -123,7 +123,7 @@ long long clock();
 static inline void __syncthreads() { emu::sync_threads(); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline void __syncwarp(unsigned = 0xffffffffu) { (void)emu::shfl(0ULL, (int)(threadIdx.x & 31)); }     // a warp-wide rendezvous (full-mask use only)
 static inline long long clock64() { return emu::clock(); }
 extern "C" void emu_misaligned(const void* p, unsigned bytes);
 template <class T> static inline T __ldg(const T* p) {

@@ -21,7 +21,8 @@ import torch.distributed as dist  # noqa: E402
 pkg = graft.load_package()
 rank, local_rank, world = pkg.parallel.env_rank()
 torch.cuda.set_device(local_rank)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 dims = tuple(int(x) for x in sys.argv[1].split(","))
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 per_setup = int(sys.argv[3]) if len(sys.argv) > 3 else 2
@@ -71,6 +72,12 @@ for rep in range(reps):
         report("rep %d step %d" % (rep, k), st, t0, state)
     st = ctx.solve_pcg(1e-8, 1e-8, itmax, history=True)
     report("rep %d resolve" % rep, st, t0, " Kx1 %s" % fp(ctx.spmv(x1)))
+soak = int(os.environ.get("DIAG_SOAK", "0"))
+if soak:
+    t0 = time.perf_counter()
+    bad_batches, bad_entries = ctx.spmv_soak(soak)
+    print("[r%d] operator soak: %d applications, %d batches of 256 with a mismatch, %d mismatching entries, %.1f s" % (
+        rank, soak, bad_batches, bad_entries, time.perf_counter() - t0), flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

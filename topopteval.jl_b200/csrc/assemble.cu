@@ -255,19 +255,22 @@ __global__ void __launch_bounds__(128) k_asm_diag(const int* __restrict__ inc_pt
 
 // ---------------------------------------------------------------------------------------------------------
 // assembly, variant ROWS (Tet4): a group of G threads owns one node row of K.
-//   pass 1  the group evaluates the geometry of the row's cells ONCE (gradients, w·λ, w·μ; ASM_CH cells per pass) into
-//           shared memory — the gather variant re-derives it for every block, 4x per (row, cell);
-//   pass 2  thread `lane` owns block slot blk_ptr[row]+lane and walks its (e,a,b) list (diagonal block: the row's own
-//           incidence list) in ascending cell order, reading g_a, g_b, wλ, wμ from shared memory:
+//   pass 1  the group evaluates the geometry of the row's cells ONCE (gradients, w·λ, w·μ; ASM_CH cells per pass) into shared
+//           memory — GATHER re-derives it for every block, 4x per (row, cell).  Layout: 14 planes of ASM_CH doubles per row, so
+//           that the threads of a group, which read different cells of the row, hit different banks (cell index = bank);
+//   pass 2  thread `lane` owns block slot blk_ptr[row]+lane and walks its contribution list in ascending cell order.  The list is
+//           the row-relative form built at set-up (mesh.cu: position of the cell in the row's incidence list, a, b in 16 bits),
+//           so a contribution is 2 bytes of index and 8 shared-memory doubles:
 //              B += wλ g_a⊗g_b + wμ g_b⊗g_a + wμ (g_a·g_b) I        (9 DMUL + 21 DFMA + 2 DADD per contribution)
+//   the diagonal block (one contribution per cell of the row, 4x an off-diagonal block) is spread over the group in pass 1.
 // Products g_a[c]·g_b[d] are shared by block (a,b) and its transpose and the accumulation order is the cell order, so K
-// stays bitwise symmetric and bit-reproducible.  ≈2.3x fewer FP64 operations per element than GATHER.
+// stays bitwise symmetric and bit-reproducible.  Groups of ≤ 32 threads live inside one warp: no CTA-wide barrier.
 // ---------------------------------------------------------------------------------------------------------
 static const int ASM_ROWS_THREADS = 128;
 static const int ASM_CH = 32;                 // cells of a row staged per pass
-static const int ASM_GEO = 14;                // doubles per staged cell: g[4][3], w·λ, w·μ
+static const int ASM_GEO = 14;                // planes per row: g[4][3], w·λ, w·μ
 
-__device__ __forceinline__ void block_acc(const double* __restrict__ ga, const double* __restrict__ gb, double wl, double wm, double acc[9]) {
+__device__ __forceinline__ void block_acc(const double ga[3], const double gb[3], double wl, double wm, double acc[9]) {
     double p[3][3];
 #pragma unroll
     for (int c = 0; c < 3; c++)
@@ -288,12 +291,12 @@ __device__ __forceinline__ void block_acc(const double* __restrict__ ga, const d
 template <int G>
 __global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __restrict__ inc_ptr, const int* __restrict__ inc,
                                                                    const int* __restrict__ blk_ptr, const int* __restrict__ blk_col,
-                                                                   const int* __restrict__ ctr_ptr, const int* __restrict__ ctr,
+                                                                   const int* __restrict__ ctr_ptr, const unsigned short* __restrict__ rctr,
                                                                    const int* __restrict__ cq, const double* __restrict__ xq, Material mat,
                                                                    double* __restrict__ val, i64 ldv, int nq, int* err) {
     constexpr int ROWS = ASM_ROWS_THREADS / G;
-    __shared__ double geo[ROWS][ASM_CH][ASM_GEO];
-    __shared__ int cell[ROWS][ASM_CH];             // e*4 + (corner of the row node in e)
+    constexpr bool IN_WARP = (G <= 32);            // the group is (part of) one warp: warp-level synchronisation suffices
+    __shared__ double geo[ROWS][ASM_GEO][ASM_CH];
     __shared__ double dpart[ASM_ROWS_THREADS][6];  // per-thread partial of the row's diagonal block (upper triangle)
     __shared__ int s_maxcells;
     const int rl = threadIdx.x / G, lane = threadIdx.x - rl * G;
@@ -305,21 +308,31 @@ __global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __
         const int b0 = __ldg(&blk_ptr[row]), b1 = __ldg(&blk_ptr[row + 1]);
         if (lane < b1 - b0) { s = b0 + lane; col = __ldg(&blk_col[s]); ci = __ldg(&ctr_ptr[s]); chi = __ldg(&ctr_ptr[s + 1]); }
     }
-    if (threadIdx.x == 0) s_maxcells = 0;
-    __syncthreads();
-    if (live && lane == 0) atomicMax(&s_maxcells, i_hi - i_lo);
-    __syncthreads();
-    const int npass = (s_maxcells + ASM_CH - 1) / ASM_CH;       // CTA-uniform: the barriers below are reached by every thread
+    int ncell = i_hi - i_lo;
+    int npass;
+    if (IN_WARP) {                                  // uniform over the warp (it may hold two or more rows)
+        int m = ncell;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        npass = (m + ASM_CH - 1) / ASM_CH;
+    } else {
+        if (threadIdx.x == 0) s_maxcells = 0;
+        __syncthreads();
+        if (live && lane == 0) atomicMax(&s_maxcells, ncell);
+        __syncthreads();
+        npass = (s_maxcells + ASM_CH - 1) / ASM_CH;
+    }
     const bool is_diag = (s >= 0 && col == row);
     double acc[9], dacc[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) { acc[k] = 0.0; dacc[k] = 0.0; }
+    unsigned ent = (ci < chi) ? (unsigned)__ldg(&rctr[ci]) : 0u;          // next contribution of this thread's block
     for (int pass = 0; pass < npass; pass++) {
-        const int k0 = i_lo + pass * ASM_CH;
-        int cnt = live ? i_hi - k0 : 0;
+        const int k0 = pass * ASM_CH;
+        int cnt = ncell - k0;
         cnt = cnt < 0 ? 0 : (cnt > ASM_CH ? ASM_CH : cnt);
         for (int k = lane; k < cnt; k += G) {
-            const int ea = __ldg(&inc[k0 + k]);
+            const int ea = __ldg(&inc[i_lo + k0 + k]);
             const int e = ea >> 2;
             double lam, mu; material_at(mat, e, lam, mu);
             int q[4]; double X[4][3], g[4][3];
@@ -327,39 +340,38 @@ __global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __
             const double det = tet_grads(X, g);
             if (!(det > 0.0)) atomicMin(err + 1, e);
             const double w = det * (1.0 / 6.0);
-            double* o = geo[rl][k];
+            const double wl = w * lam, wm = w * mu;
 #pragma unroll
             for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int i = 0; i < 3; i++) o[3 * a + i] = g[a][i];
-            o[12] = w * lam; o[13] = w * mu;
-            cell[rl][k] = ea;
+                for (int i = 0; i < 3; i++) geo[rl][3 * a + i][k] = g[a][i];
+            geo[rl][12][k] = wl; geo[rl][13][k] = wm;
             // the diagonal block has a contribution from every cell of the row (4x the work of an off-diagonal block): it is
             // spread over the group here — each thread adds its cells (ascending), the partials are summed in lane order below
-            const double* ga = o + 3 * (ea & 3);
-            block_acc(ga, ga, o[12], o[13], dacc);
+            double ga[3];
+            sel4(g, ea & 3, ga);
+            block_acc(ga, ga, wl, wm, dacc);
         }
-        __syncthreads();
-        if (s >= 0 && cnt > 0) {
-            if (!is_diag) {
-                const int e_last = cell[rl][cnt - 1] >> 2;
-                int k = 0;
-                while (ci < chi) {
-                    int e, a, b; ctr_unpack<4>(__ldg(&ctr[ci]), e, a, b);
-                    if (e > e_last) break;                                   // belongs to a later pass
-                    while (k < cnt && (cell[rl][k] >> 2) != e) k++;
-                    if (k >= cnt) { atomicExch(err + 2, 1); ci = chi; break; }   // lists out of step (cannot happen with lists built by mesh.cu)
-                    const double* o = geo[rl][k];
-                    block_acc(o + 3 * a, o + 3 * b, o[12], o[13], acc);
-                    ci++;
-                }
+        if (IN_WARP) __syncwarp(); else __syncthreads();
+        if (!is_diag) {
+            while (ci < chi) {
+                const int k = (int)(ent >> 4) - k0;
+                if (k >= cnt) break;                                     // belongs to a later pass
+                const int a = (ent >> 2) & 3, b = ent & 3;
+                ci++;
+                const unsigned nxt = (ci < chi) ? (unsigned)__ldg(&rctr[ci]) : 0u;
+                const double (*gr)[ASM_CH] = geo[rl];
+                const double ga[3] = {gr[3 * a][k], gr[3 * a + 1][k], gr[3 * a + 2][k]};
+                const double gb[3] = {gr[3 * b][k], gr[3 * b + 1][k], gr[3 * b + 2][k]};
+                block_acc(ga, gb, gr[12][k], gr[13][k], acc);
+                ent = nxt;
             }
         }
-        __syncthreads();
+        if (IN_WARP) __syncwarp(); else __syncthreads();
     }
     dpart[threadIdx.x][0] = dacc[0]; dpart[threadIdx.x][1] = dacc[1]; dpart[threadIdx.x][2] = dacc[2];
     dpart[threadIdx.x][3] = dacc[4]; dpart[threadIdx.x][4] = dacc[5]; dpart[threadIdx.x][5] = dacc[8];
-    __syncthreads();
+    if (IN_WARP) __syncwarp(); else __syncthreads();
     if (is_diag) {
         double d[6] = {0, 0, 0, 0, 0, 0};
         for (int l = 0; l < G; l++) {
@@ -408,9 +420,9 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
     TRY(ensure_vectors(ctx));
     if (variant == TOE_ASM_AUTO) variant = TOE_ASM_GATHER;
     if (variant != TOE_ASM_ATOMIC && variant != TOE_ASM_GATHER && variant != TOE_ASM_ROWS) return toe_fail(ctx, TOE_ERR_ARG, "unknown assembly variant %d", variant);
-    // ROWS is written for Tet4 and rows of at most 64 blocks; everything else takes the GATHER kernels
-    if (variant == TOE_ASM_ROWS && (ctx->npc != 4 || ctx->max_deg > 64)) variant = TOE_ASM_GATHER;
     if (variant != TOE_ASM_ATOMIC) TRY(mesh_build_contrib(ctx));      // one-off per mesh, outside the timed stage
+    // ROWS is written for Tet4, rows of at most 64 blocks and < 4096 cells around a node; everything else takes the GATHER kernels
+    if (variant == TOE_ASM_ROWS && (ctx->npc != 4 || ctx->max_deg > 64 || !ctx->have_rctr)) variant = TOE_ASM_GATHER;
     size_t n = 3 * (size_t)ctx->nq;
     i64 nnzb = ctx->nnzb, ldv = ctx->ldv;
     if (ctx->val.n < 9 * (size_t)ldv + 16) {
@@ -444,7 +456,7 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
     } else if (variant == TOE_ASM_ROWS) {
         CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
 #define ROWS_ARGS (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const int*)ctx->ctr_ptr.p, \
-        (const int*)ctx->ctr.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p, amat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p
+        (const unsigned short*)ctx->rctr.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p, amat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p
         int gmin = 0;                                         // TOE_ASM_ROWS_G=32|64 forces a wider group (tests)
         if (const char* eg = getenv("TOE_ASM_ROWS_G")) gmin = atoi(eg);
         if (ctx->max_deg <= 16 && gmin <= 16)      LAUNCH(ctx, k_asm_rows_tet<16>, div_up(ctx->nq, ASM_ROWS_THREADS / 16), ASM_ROWS_THREADS, 0, ROWS_ARGS);

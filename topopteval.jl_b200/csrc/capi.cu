@@ -16,6 +16,7 @@ int get_pattern(toe_ctx* ctx, int64_t* colptr_host, int64_t* rowval_host);
 int get_values(toe_ctx* ctx, double* nzval_host);
 int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap);
 int time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out);
+int spmv_soak(toe_ctx* ctx, int matrix_free, i64 reps, i64* mismatching_reps, i64* mismatching_entries);
 int energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem_host);
 int energy_assembled(toe_ctx* ctx, double* half_uKu);
 int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell);
@@ -365,6 +366,14 @@ int toe_spmv(toe_ctx* ctx, const double* x, double* y, int matrix_free) {
 }
 
 int toe_time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out) { GUARD(ctx); return time_spmv(ctx, matrix_free, reps, seconds_out, bytes_out); }
+int toe_spmv_soak(toe_ctx* ctx, int matrix_free, int64_t reps, int64_t* mismatching_batches, int64_t* mismatching_entries) {
+    GUARD(ctx);
+    i64 a = 0, b = 0;
+    int st = spmv_soak(ctx, matrix_free, reps, &a, &b);
+    if (mismatching_batches) *mismatching_batches = a;
+    if (mismatching_entries) *mismatching_entries = b;
+    return st;
+}
 
 int toe_comm_unique_id(char id_out[128]) {
     std::lock_guard<std::mutex> lk(g_mutex);

@@ -108,6 +108,10 @@ struct toe_ctx {
     i64 ldv = 0;              // stride between the 9 value planes (>= nnzb, multiple of 16)
     // block -> contributing (e,a,b) lists, off-diagonal blocks only (entries e*64 + a*8 + b, ascending e)
     DevBuf<int> ctr_ptr, ctr;
+    // the same lists relative to the row (Tet4, ROWS assembly): (position of the cell in the row node's incidence list) << 4 | a << 2 | b
+    DevBuf<unsigned short> rctr;
+    bool have_rctr = false;
+    int max_inc = 0;          // largest number of cells around a node
     // tiles of consecutive cells for the matrix-free operator (ebe_tile.cu)
     bool have_tiles = false;
     int ntiles = 0, tile_elems = 0, tile_max_nodes = 0;

@@ -281,7 +281,7 @@ int mesh_build_pattern(toe_ctx* ctx) {
 template <int NPC, bool FILL>
 __global__ void k_contrib(const int* __restrict__ blk_ptr, const int* __restrict__ blk_col, const int* __restrict__ inc_ptr,
                           const int* __restrict__ inc, const int* __restrict__ cq, int* __restrict__ cnt,
-                          const int* __restrict__ ctr_ptr, int* __restrict__ ctr, int nq) {
+                          const int* __restrict__ ctr_ptr, int* __restrict__ ctr, unsigned short* __restrict__ rctr, int nq) {
     // thread per (row q, k-th block of the row): rows are short, so a flat loop over slots with a row lookup
     // would need a search; instead a warp-strided loop inside the row keeps it simple.
     int q = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);     // 8 lanes per row
@@ -299,10 +299,23 @@ __global__ void k_contrib(const int* __restrict__ blk_ptr, const int* __restrict
             const int* c = cq + (size_t)e * NPC;
 #pragma unroll
             for (int b = 0; b < NPC; b++)
-                if (c[b] == col) { if (FILL) ctr[base + n] = ctr_pack<NPC>(e, a, b); n++; }
+                if (c[b] == col) {
+                    if (FILL) {
+                        ctr[base + n] = ctr_pack<NPC>(e, a, b);
+                        if (rctr) rctr[base + n] = (unsigned short)(((k - lo) << 4) | (a << 2) | b);     // row-relative form (Tet4, < 4096 cells per node)
+                    }
+                    n++;
+                }
         }
         if (!FILL) cnt[s] = n;
     }
+}
+
+__global__ void k_max_inc(const int* __restrict__ inc_ptr, int nq, int* out) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = q < nq ? inc_ptr[q + 1] - inc_ptr[q] : 0;
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, v);
 }
 
 int mesh_build_contrib(toe_ctx* ctx) {
@@ -314,12 +327,20 @@ int mesh_build_contrib(toe_ctx* ctx) {
     CU(ctx->ctr_ptr.alloc(ctx->nnzb + 1));
     unsigned grid = div_up(nq, 16);
 #define ARGS(cntp, ptrp, ctrp) (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, \
-        (const int*)ctx->cq.p, cntp, ptrp, ctrp, nq
+        (const int*)ctx->cq.p, cntp, ptrp, ctrp, rctrp, nq
+    unsigned short* rctrp = nullptr;
     if (ctx->npc == 4) LAUNCH(ctx, (k_contrib<4, false>), grid, 128, 0, ARGS(ctx->ctr_ptr.p, (const int*)nullptr, (int*)nullptr));
     else               LAUNCH(ctx, (k_contrib<8, false>), grid, 128, 0, ARGS(ctx->ctr_ptr.p, (const int*)nullptr, (int*)nullptr));
     i64 total = 0;
     TRY(scan_exclusive_i32(ctx, ctx->ctr_ptr.p, ctx->ctr_ptr.p, ctx->nnzb, &total));
     CU(ctx->ctr.alloc(total));
+    // largest incidence list: the row-relative lists hold the list position in 12 bits
+    CU(cudaMemsetAsync(ctx->errflag.p + 3, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_max_inc, div_up(nq, 256), 256, 0, (const int*)ctx->inc_ptr.p, nq, ctx->errflag.p + 3);
+    CU(cudaMemcpyAsync(&ctx->max_inc, ctx->errflag.p + 3, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_rctr = (ctx->npc == 4 && ctx->max_inc < 4096);
+    if (ctx->have_rctr) { CU(ctx->rctr.alloc(total)); rctrp = ctx->rctr.p; }
     if (ctx->npc == 4) LAUNCH(ctx, (k_contrib<4, true>), grid, 128, 0, ARGS((int*)nullptr, (const int*)ctx->ctr_ptr.p, ctx->ctr.p));
     else               LAUNCH(ctx, (k_contrib<8, true>), grid, 128, 0, ARGS((int*)nullptr, (const int*)ctx->ctr_ptr.p, ctx->ctr.p));
 #undef ARGS

@@ -708,6 +708,43 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     return TOE_OK;
 }
 
+// number of entries of a that differ from b (bitwise)
+__global__ void __launch_bounds__(VEC_THREADS) k_count_diff(const double* __restrict__ a, const double* __restrict__ b, size_t n, unsigned long long* count) {
+    unsigned long long c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (__double_as_longlong(a[i]) != __double_as_longlong(b[i])) c++;
+    if (c) atomicAdd(count, c);
+}
+
+// Soak test of the operator (diagnostic): y0 = A x once, then `reps` more applications of the same product (local product + interface
+// sum on a partitioned ctx), each compared bit for bit with y0 on the device.  Every kernel of the path is deterministic, so any
+// mismatch is a fault of the machinery (pipeline protocol, exchange, hardware), not rounding.
+int spmv_soak(toe_ctx* ctx, int matrix_free, i64 reps, i64* mismatching_reps, i64* mismatching_entries) {
+    TRY(ensure_vectors(ctx));
+    if (!ctx->have_solution) return toe_fail(ctx, TOE_ERR_STATE, "toe_spmv_soak: needs a stored vector (solve or toe_set_solution first)");
+    size_t n = 3 * (size_t)ctx->nq;
+    DevBuf<unsigned long long> cnt; CU(cnt.alloc(2));
+    CU(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    TRY(dist_align(ctx));
+    TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, false));
+    TRY(dist_post_spmv(ctx, ctx->tmp.p));
+    i64 bad_reps = 0;
+    unsigned long long prev = 0, h[2];
+    for (i64 k = 0; k < reps; k++) {
+        TRY(op_launch(ctx, ctx->u.p, ctx->Ap.p, matrix_free, nullptr, false));
+        TRY(dist_post_spmv(ctx, ctx->Ap.p));
+        LAUNCH(ctx, k_count_diff, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->Ap.p, (const double*)ctx->tmp.p, n, cnt.p);
+        if ((k & 255) == 255 || k == reps - 1) {              // host check every 256 launches: counts the launches-with-a-fault to within a batch
+            CU(cudaMemcpyAsync(h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (h[0] != prev) { bad_reps++; prev = h[0]; }
+        }
+    }
+    if (mismatching_reps) *mismatching_reps = bad_reps;
+    if (mismatching_entries) *mismatching_entries = (i64)prev;
+    return TOE_OK;
+}
+
 int time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out) {
     TRY(ensure_vectors(ctx));
     if (reps < 1) reps = 1;
