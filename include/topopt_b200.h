@@ -198,10 +198,14 @@ int toe_spmv(toe_ctx* ctx, const double* x, double* y, int matrix_free);
 /* times `reps` back-to-back operator applications on device vectors; returns average seconds and the
  * algorithmic bytes of one application. */
 int toe_time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out);
-/* diagnostic: applies the operator to the stored vector u `reps`+1 times (on a partitioned ctx: local product + interface sum) and
- * compares every result bit for bit with the first on the device.  The path is deterministic, so both counts must be 0:
- * mismatching_batches = batches of 256 applications in which a difference appeared, mismatching_entries = differing entries in total. */
-int toe_spmv_soak(toe_ctx* ctx, int matrix_free, int64_t reps, int64_t* mismatching_batches, int64_t* mismatching_entries);
+/* diagnostic: applies the operator to the stored vector u `reps`+1 times and compares every result bit for bit with the first on the
+ * device.  what: 1 = local product only, 2 = interface exchange only, 3 = product + exchange (2, 3: partitioned ctx).  The path is
+ * deterministic, so both counts must be 0: mismatching_batches = batches of 256 applications in which a difference appeared,
+ * mismatching_entries = differing entries in total. */
+/* diagnostic (partitioned Jacobi-PCG run with TOE_CG_TRACE=1 in the environment): 4 doubles per iteration j —
+ * {γ_j, δ_j as summed over the ranks, this rank's partial of γ_j, this rank's partial of δ_j}; out holds 4*iterations doubles */
+int toe_debug_cg_trace(toe_ctx* ctx, double* out, int64_t iterations);
+int toe_spmv_soak(toe_ctx* ctx, int matrix_free, int what, int64_t reps, int64_t* mismatching_batches, int64_t* mismatching_entries);
 
 /* ---- multi-GPU: one ctx per GPU / process, element-based domain decomposition --------------------------- */
 /* NCCL (dlopen'ed libnccl.so.2) send/recv for the interface-DOF exchange and allreduce for the CG scalars.

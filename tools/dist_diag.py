@@ -34,6 +34,8 @@ ctx = pkg.parallel.create_distributed_context(dist, local_rank) if world > 1 els
 pres = None
 x1 = x2 = None
 ref_hist = None
+ref_trace = None
+TRACE = os.environ.get("TOE_CG_TRACE") == "1" and world > 1
 
 
 def fp(a):
@@ -50,6 +52,24 @@ def report(tag, st, t0, state):
         m = min(len(h), len(ref_hist))
         d = np.nonzero(h[:m] != ref_hist[:m])[0]
         div = " leaves_ref_at %s" % (int(d[0]) if len(d) else ("never" if len(h) == len(ref_hist) else "len %d/%d" % (len(h), len(ref_hist))))
+    if TRACE:
+        global ref_trace
+        tr = ctx.cg_trace(st["niter"] + 1)
+        if ref_trace is None and st["converged"]:
+            ref_trace = tr.copy()
+        elif ref_trace is not None:
+            m = min(len(tr), len(ref_trace))
+            bad = np.nonzero(np.any(tr[:m] != ref_trace[:m], axis=1))[0]
+            if len(bad):
+                j = int(bad[0])
+                cols = ["gamma_sum", "delta_sum", "gamma_partial", "delta_partial"]
+                np.set_printoptions(precision=17)
+                print("[r%d] TRACE first mismatch at iteration %d, columns %s" % (rank, j, [cols[k] for k in range(4) if tr[j, k] != ref_trace[j, k]]), flush=True)
+                for jj in range(max(0, j - 1), min(m, j + 3)):
+                    print("[r%d]   it %d got %s" % (rank, jj, np.array2string(tr[jj], floatmode="unique")), flush=True)
+                    print("[r%d]   it %d ref %s" % (rank, jj, np.array2string(ref_trace[jj], floatmode="unique")), flush=True)
+                nb = np.nonzero(np.any(tr[:m, 2:] != ref_trace[:m, 2:], axis=1))[0]
+                print("[r%d]   first mismatching LOCAL partial at iteration %s" % (rank, int(nb[0]) if len(nb) else None), flush=True)
     e, c, _ = ctx.energy()
     print("[r%d] %s niter %d conv %d brk %d rst %d solve_s %.3f relres %.3e energy %.10f hist %s%s%s wall %.2f" % (
         rank, tag, st["niter"], st["converged"], st["breakdown"], st.get("restarts", 0), st["solve_seconds"], st["rel_res_l2"], e, fp(h), div, state,
@@ -73,11 +93,11 @@ for rep in range(reps):
     st = ctx.solve_pcg(1e-8, 1e-8, itmax, history=True)
     report("rep %d resolve" % rep, st, t0, " Kx1 %s" % fp(ctx.spmv(x1)))
 soak = int(os.environ.get("DIAG_SOAK", "0"))
-if soak:
+for what in ((1, 2, 3) if world > 1 else (1,)) if soak else ():
     t0 = time.perf_counter()
-    bad_batches, bad_entries = ctx.spmv_soak(soak)
-    print("[r%d] operator soak: %d applications, %d batches of 256 with a mismatch, %d mismatching entries, %.1f s" % (
-        rank, soak, bad_batches, bad_entries, time.perf_counter() - t0), flush=True)
+    bad_batches, bad_entries = ctx.spmv_soak(soak, what)
+    print("[r%d] operator soak (%s): %d applications, %d batches of 256 with a mismatch, %d mismatching entries, %.1f s" % (
+        rank, {1: "local product", 2: "exchange", 3: "product + exchange"}[what], soak, bad_batches, bad_entries, time.perf_counter() - t0), flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

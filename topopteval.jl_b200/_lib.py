@@ -89,7 +89,8 @@ SIGNATURES = {
     "toe_calculate_stresses_lame_per_cell": (C.c_int, [_P, _D, _D, _D, _D, _D, _D, _I64]),
     "toe_spmv": (C.c_int, [_P, _D, _D, C.c_int]),
     "toe_time_spmv": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
-    "toe_spmv_soak": (C.c_int, [_P, C.c_int, C.c_int64, _I64, _I64]),
+    "toe_debug_cg_trace": (C.c_int, [_P, _D, C.c_int64]),
+    "toe_spmv_soak": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _I64, _I64]),
     "toe_comm_unique_id": (C.c_int, [C.c_char_p]),
     "toe_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p]),
     "toe_set_mesh_distributed": (C.c_int, [_P, C.c_int64, _D, C.c_int64, C.c_int, _I64]),
@@ -413,10 +414,16 @@ class Context:
         self._ck(self.lib.toe_time_spmv(self.h, 1 if matrix_free else 0, reps, C.byref(s), C.byref(b)))
         return s.value, b.value
 
-    def spmv_soak(self, reps, matrix_free=False):
-        """(batches with a mismatch, mismatching entries) of `reps` repeated operator applications against the first one"""
+    def cg_trace(self, iterations):
+        out = np.zeros((int(iterations), 4))
+        self._ck(self.lib.toe_debug_cg_trace(self.h, _dp(out), int(iterations)))
+        return out
+
+    def spmv_soak(self, reps, what=1, matrix_free=False):
+        """(batches with a mismatch, mismatching entries) of `reps` repeated operator applications against the first one;
+        what: 1 = local product, 2 = interface exchange, 3 = both"""
         a, b = C.c_int64(), C.c_int64()
-        self._ck(self.lib.toe_spmv_soak(self.h, 1 if matrix_free else 0, int(reps), C.byref(a), C.byref(b)))
+        self._ck(self.lib.toe_spmv_soak(self.h, 1 if matrix_free else 0, int(what), int(reps), C.byref(a), C.byref(b)))
         return a.value, b.value
 
     def timer_start(self):

@@ -16,7 +16,8 @@ int get_pattern(toe_ctx* ctx, int64_t* colptr_host, int64_t* rowval_host);
 int get_values(toe_ctx* ctx, double* nzval_host);
 int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_pcg_stats* stats, double* history, i64 history_cap);
 int time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out);
-int spmv_soak(toe_ctx* ctx, int matrix_free, i64 reps, i64* mismatching_reps, i64* mismatching_entries);
+int cg_trace(toe_ctx* ctx, double* out, i64 iterations);
+int spmv_soak(toe_ctx* ctx, int matrix_free, int what, i64 reps, i64* mismatching_batches, i64* mismatching_entries);
 int energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem_host);
 int energy_assembled(toe_ctx* ctx, double* half_uKu);
 int stresses(toe_ctx* ctx, double* sigma_host, double* vm_host, double* max_vm, int64_t* max_cell);
@@ -366,10 +367,11 @@ int toe_spmv(toe_ctx* ctx, const double* x, double* y, int matrix_free) {
 }
 
 int toe_time_spmv(toe_ctx* ctx, int matrix_free, int reps, double* seconds_out, double* bytes_out) { GUARD(ctx); return time_spmv(ctx, matrix_free, reps, seconds_out, bytes_out); }
-int toe_spmv_soak(toe_ctx* ctx, int matrix_free, int64_t reps, int64_t* mismatching_batches, int64_t* mismatching_entries) {
+int toe_debug_cg_trace(toe_ctx* ctx, double* out, int64_t iterations) { GUARD(ctx); if (!out) return TOE_ERR_ARG; return cg_trace(ctx, out, iterations); }
+int toe_spmv_soak(toe_ctx* ctx, int matrix_free, int what, int64_t reps, int64_t* mismatching_batches, int64_t* mismatching_entries) {
     GUARD(ctx);
     i64 a = 0, b = 0;
-    int st = spmv_soak(ctx, matrix_free, reps, &a, &b);
+    int st = spmv_soak(ctx, matrix_free, what, reps, &a, &b);
     if (mismatching_batches) *mismatching_batches = a;
     if (mismatching_entries) *mismatching_entries = b;
     return st;

@@ -146,6 +146,7 @@ struct toe_ctx {
     DevBuf<unsigned int> counters;
     DevBuf<CGScalars> cgs;
     DevBuf<double> hist;
+    DevBuf<double> cg_trace;      // diagnostic (TOE_CG_TRACE=1, partitioned CG): per iteration {γ, δ summed over ranks; this rank's γ, δ partials}
     DevBuf<int> errflag;
 
     // CUDA graph of a batch of PCG iterations

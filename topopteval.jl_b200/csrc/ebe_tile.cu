@@ -164,7 +164,7 @@ int mesh_build_tiles(toe_ctx* ctx) {
 // operator
 // ---------------------------------------------------------------------------------------------------------
 template <int NPC, bool MASK>
-__global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restrict__ tile_off, const int* __restrict__ tile_m, const int* __restrict__ tile_nodes,
+__global__ void __launch_bounds__(TILE_REFS / NPC, NPC == 4 ? 4 : 1) k_ebe_tile(const int* __restrict__ tile_off, const int* __restrict__ tile_m, const int* __restrict__ tile_nodes,
                                                               const unsigned short* __restrict__ lconn, const unsigned short* __restrict__ inc_sorted,
                                                               const unsigned short* __restrict__ nstart, const double* __restrict__ xq, Material mat,
                                                               const unsigned char* __restrict__ dflag, const double* __restrict__ x,
@@ -177,10 +177,16 @@ __global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restr
     const i64 e0 = (i64)t * TE;
     const int nel = (int)min((i64)TE, ne - e0);
     const int nref = nel * NPC;
-    double* scratch = sm;                        // [TILE_REFS][3]: (Kₑxₑ)_a per ref
-    double* Xs = sm + 3 * TILE_REFS;             // [m][3] coordinates
-    double* xs = Xs + 3 * m;                     // [m][3] x
-    unsigned short* s_inc = reinterpret_cast<unsigned short*>(xs + 3 * m);      // [TILE_REFS] node-sorted refs
+    // Shared-memory layout chosen for the bank structure (round-1 ncu: 62 % of this kernel's shared-memory wavefronts were bank
+    // conflicts and l1tex ran at 87 % of peak — the kernel was shared-memory-bandwidth bound):
+    //   sA[a][cell] double2 = first two components of (Kₑxₑ)_a, sB[a][cell] = the third: a thread's stores go to consecutive
+    //                addresses of consecutive threads (the old [ref][3] layout had a 96-byte stride = 4-way conflicts);
+    //   nd[node]     6 doubles (X0 X1 X2 x0 x1 x2) = three 16-byte loads per corner instead of six 8-byte ones; the 48-byte stride
+    //                maps 8 consecutive nodes onto the 8 distinct 16-byte bank groups.
+    double2* sA = reinterpret_cast<double2*>(sm);                               // [NPC][TE]
+    double* sB = sm + 2 * TILE_REFS;                                            // [NPC][TE]
+    double* nd = sm + 3 * TILE_REFS;                                            // [m][6]
+    unsigned short* s_inc = reinterpret_cast<unsigned short*>(nd + 6 * m);      // [TILE_REFS] node-sorted refs
     unsigned short* s_nst = s_inc + TILE_REFS;                                  // [m] first ref of each local node
     // every global load of the tile is issued before the first barrier: metadata, connectivity, material, node data
     uint2 lc2 = make_uint2(0, 0); uint4 lc4 = make_uint4(0, 0, 0, 0);
@@ -204,46 +210,51 @@ __global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restr
 #pragma unroll
             for (int k = 0; k < 3; k++) if (dflag[3 * (size_t)q + k]) v[k] = 0.0;
         }
-#pragma unroll
-        for (int k = 0; k < 3; k++) { Xs[3 * j + k] = c[k]; xs[3 * j + k] = v[k]; }
+        double2* o = reinterpret_cast<double2*>(nd + 6 * j);
+        o[0] = make_double2(c[0], c[1]); o[1] = make_double2(c[2], v[0]); o[2] = make_double2(v[1], v[2]);
     }
     __syncthreads();
+    const double2* nd2 = reinterpret_cast<const double2*>(nd);
     if (tid < nel) {
         int l[NPC];
         if (NPC == 4) {
             uint2 p = lc2;
             l[0] = p.x & 0xffff; l[1] = p.x >> 16; l[2] = p.y & 0xffff; l[3] = p.y >> 16;
-            double X[4][3], g[4][3];
+            double X[4][3], xv[4][3], g[4][3];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) X[a][k] = Xs[3 * l[a] + k];
+            for (int a = 0; a < 4; a++) {
+                const double2 p0 = nd2[3 * l[a]], p1 = nd2[3 * l[a] + 1], p2 = nd2[3 * l[a] + 2];
+                X[a][0] = p0.x; X[a][1] = p0.y; X[a][2] = p1.x; xv[a][0] = p1.y; xv[a][1] = p2.x; xv[a][2] = p2.y;
+            }
             double det = tet_grads(X, g);
             double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
             for (int b = 0; b < 4; b++)
 #pragma unroll
                 for (int c2 = 0; c2 < 3; c2++) {
-                    double xv = xs[3 * l[b] + c2];
 #pragma unroll
-                    for (int i2 = 0; i2 < 3; i2++) H[c2][i2] += xv * g[b][i2];
+                    for (int i2 = 0; i2 < 3; i2++) H[c2][i2] += xv[b][c2] * g[b][i2];
                 }
             double S[3][3]; hooke_from_grad(H, lam, mu, S);
             double w = det * (1.0 / 6.0);
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+            for (int a = 0; a < 4; a++) {
+                double r[3];
 #pragma unroll
-                for (int c2 = 0; c2 < 3; c2++)
-                    scratch[3 * (4 * tid + a) + c2] = w * (S[c2][0] * g[a][0] + S[c2][1] * g[a][1] + S[c2][2] * g[a][2]);
+                for (int c2 = 0; c2 < 3; c2++) r[c2] = w * (S[c2][0] * g[a][0] + S[c2][1] * g[a][1] + S[c2][2] * g[a][2]);
+                sA[a * TE + tid] = make_double2(r[0], r[1]); sB[a * TE + tid] = r[2];
+            }
         } else {
             uint4 p = lc4;
             l[0] = p.x & 0xffff; l[1] = p.x >> 16; l[2] = p.y & 0xffff; l[3] = p.y >> 16;
             l[4] = p.z & 0xffff; l[5] = p.z >> 16; l[6] = p.w & 0xffff; l[7] = p.w >> 16;
             double X[8][3], xe[8][3], out[8][3];
 #pragma unroll
-            for (int a = 0; a < 8; a++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) { X[a][k] = Xs[3 * l[a] + k]; xe[a][k] = xs[3 * l[a] + k]; out[a][k] = 0.0; }
+            for (int a = 0; a < 8; a++) {
+                const double2 p0 = nd2[3 * l[a]], p1 = nd2[3 * l[a] + 1], p2 = nd2[3 * l[a] + 2];
+                X[a][0] = p0.x; X[a][1] = p0.y; X[a][2] = p1.x; xe[a][0] = p1.y; xe[a][1] = p2.x; xe[a][2] = p2.y;
+                out[a][0] = out[a][1] = out[a][2] = 0.0;
+            }
             for (int gp = 0; gp < 8; gp++) {
                 double g[8][3], N[8];
                 double det = hex_grads_at(X, gp, g, N);
@@ -261,9 +272,7 @@ __global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restr
                     for (int c2 = 0; c2 < 3; c2++) out[a][c2] += det * (S[c2][0] * g[a][0] + S[c2][1] * g[a][1] + S[c2][2] * g[a][2]);
             }
 #pragma unroll
-            for (int a = 0; a < 8; a++)
-#pragma unroll
-                for (int c2 = 0; c2 < 3; c2++) scratch[3 * (8 * tid + a) + c2] = out[a][c2];
+            for (int a = 0; a < 8; a++) { sA[a * TE + tid] = make_double2(out[a][0], out[a][1]); sB[a * TE + tid] = out[a][2]; }
         }
     }
     __syncthreads();
@@ -272,8 +281,10 @@ __global__ void __launch_bounds__(TILE_REFS / NPC) k_ebe_tile(const int* __restr
         int hi = j + 1 < m ? (int)s_nst[j + 1] : nref;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int p = lo; p < hi; p++) {                          // refs of this node in ascending (cell, corner) order
-            int ref = s_inc[p];
-            s0 += scratch[3 * ref]; s1 += scratch[3 * ref + 1]; s2 += scratch[3 * ref + 2];
+            const int ref = s_inc[p];
+            const int slot = (ref & (NPC - 1)) * TE + (ref / NPC);
+            const double2 v = sA[slot];
+            s0 += v.x; s1 += v.y; s2 += sB[slot];
         }
         double* o = stage + 3 * (size_t)(off + j);
         o[0] = s0; o[1] = s1; o[2] = s2;

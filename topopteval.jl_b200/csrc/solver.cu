@@ -475,7 +475,8 @@ __global__ void k_cgcg_fin_init(CGScalars* cg, double atol, double rtol, i64 itm
 __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restrict__ Minv, const double* __restrict__ w, double* __restrict__ z,
                                                           double* __restrict__ p, double* __restrict__ s, double* __restrict__ x, double* __restrict__ r,
                                                           size_t n, CGScalars* cg, int par, double* hist, i64 hist_cap,
-                                                          const unsigned char* __restrict__ owned, double* partials, unsigned int* counter, int l2) {
+                                                          const unsigned char* __restrict__ owned, double* partials, unsigned int* counter, int l2,
+                                                          double* trace) {
     __shared__ double red[32];
     if (cg->done) return;
     const i64 j = cg->iter;                        // advanced once, by the last block of this launch, after every block has read it
@@ -489,6 +490,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restri
     const bool brk = !(denom > 0.0) && !conv && !tired;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (j < hist_cap) hist[j] = res;
+        if (trace && j < hist_cap) { trace[4 * j] = g; trace[4 * j + 1] = dl; }
         cg->gamma = g; cg->res = res;
         if (conv) { cg->converged = 1; cg->done = 1; }
         else if (tired) cg->done = 1;
@@ -513,7 +515,16 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgcg_vec(const double* __restri
     gs = block_sum(gs, red);
     ns = block_sum(ns, red);
     double tot, tot2;
-    if (grid_sum2_last_block(gs, ns, partials, counter, red, &tot, &tot2)) { cg->gd[par ^ 1][0] = tot; cg->gd[par ^ 1][2] = tot2; cg->iter = j + 1; }
+    if (grid_sum2_last_block(gs, ns, partials, counter, red, &tot, &tot2)) {
+        cg->gd[par ^ 1][0] = tot; cg->gd[par ^ 1][2] = tot2; cg->iter = j + 1;
+        if (trace && j + 1 < hist_cap) trace[4 * (j + 1) + 2] = tot;
+    }
+}
+// diagnostic: this rank's δ partial of the iteration that is being closed (after the operator, before the exchange)
+__global__ void k_trace_delta(const CGScalars* cg, int par, double* trace, i64 cap) {
+    if (threadIdx.x || blockIdx.x || cg->done) return;
+    const i64 j = cg->iter;                      // already advanced by k_cgcg_vec
+    if (j < cap) trace[4 * j + 3] = cg->gd[par ^ 1][1];
 }
 int dist_exchange_allreduce(toe_ctx* ctx, double* y, double* scal, int count);
 int dist_check_exchange(toe_ctx* ctx);     // dist.cu: interface sum of y + allreduce of scal in ONE NCCL group
@@ -525,8 +536,9 @@ static int cgcg_iteration(toe_ctx* ctx, int matrix_free, size_t n, i64 hist_cap,
     CGScalars* cg = ctx->cgs.p;
     double* z = ctx->cg_z.p; double* w = ctx->Ap.p;
     LAUNCH(ctx, k_cgcg_vec, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->Minv.p, (const double*)w, z, ctx->p.p, ctx->cg_s.p, ctx->u.p, ctx->r.p,
-           n, cg, par, ctx->hist.p, hist_cap, ctx->owned, ctx->partials.p, ctx->counters.p + 8, l2);
+           n, cg, par, ctx->hist.p, hist_cap, ctx->owned, ctx->partials.p, ctx->counters.p + 8, l2, ctx->cg_trace.p);
     TRY(op_launch(ctx, z, w, matrix_free, cg, true, &cg->done, &cg->gd[par ^ 1][1]));
+    if (ctx->cg_trace.p) LAUNCH(ctx, k_trace_delta, 1, 32, 0, (const CGScalars*)cg, par, ctx->cg_trace.p, hist_cap);
     TRY(dist_exchange_allreduce(ctx, w, &cg->gd[par ^ 1][0], l2 ? 3 : 2));
     return TOE_OK;
 }
@@ -587,6 +599,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
     const i64 hist_cap = HIST_CAP;            // fixed: pointer and capacity are baked into the captured graph
     CU(ctx->hist.alloc(hist_cap));
     if (dist) { CU(ctx->cg_s.alloc(n)); CU(ctx->cg_z.alloc(n)); }
+    if (dist && getenv("TOE_CG_TRACE")) { CU(ctx->cg_trace.alloc(4 * (size_t)hist_cap)); CU(cudaMemsetAsync(ctx->cg_trace.p, 0, 4 * (size_t)hist_cap * sizeof(double), ctx->stream)); }
     if (!ctx->cgs_host) CU(cudaMallocHost((void**)&ctx->cgs_host, sizeof(CGScalars)));
     i64 launches0 = ctx->launches;
     const int per_iter = two_level ? 6 : (dist ? 4 : 3);
@@ -716,32 +729,45 @@ __global__ void __launch_bounds__(VEC_THREADS) k_count_diff(const double* __rest
     if (c) atomicAdd(count, c);
 }
 
-// Soak test of the operator (diagnostic): y0 = A x once, then `reps` more applications of the same product (local product + interface
-// sum on a partitioned ctx), each compared bit for bit with y0 on the device.  Every kernel of the path is deterministic, so any
-// mismatch is a fault of the machinery (pipeline protocol, exchange, hardware), not rounding.
-int spmv_soak(toe_ctx* ctx, int matrix_free, i64 reps, i64* mismatching_reps, i64* mismatching_entries) {
+// Soak test of the operator (diagnostic): the product of the stored vector u is formed once, then `reps` more times, each result
+// compared bit for bit with the first on the device.  Every kernel of the path is deterministic, so any mismatch is a fault of the
+// machinery (pipeline protocol, exchange, hardware), not rounding.  what: 1 = local product only, 2 = interface exchange only (the
+// same local product is re-exchanged), 3 = product + exchange (what one PCG iteration does); 2 and 3 need a partitioned ctx.
+int spmv_soak(toe_ctx* ctx, int matrix_free, int what, i64 reps, i64* mismatching_batches, i64* mismatching_entries) {
     TRY(ensure_vectors(ctx));
     if (!ctx->have_solution) return toe_fail(ctx, TOE_ERR_STATE, "toe_spmv_soak: needs a stored vector (solve or toe_set_solution first)");
+    if (what < 1 || what > 3) return toe_fail(ctx, TOE_ERR_ARG, "toe_spmv_soak: what must be 1, 2 or 3");
     size_t n = 3 * (size_t)ctx->nq;
     DevBuf<unsigned long long> cnt; CU(cnt.alloc(2));
     CU(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
     TRY(dist_align(ctx));
-    TRY(op_launch(ctx, ctx->u.p, ctx->tmp.p, matrix_free, nullptr, false));
-    TRY(dist_post_spmv(ctx, ctx->tmp.p));
-    i64 bad_reps = 0;
+    double* local_ref = ctx->r.p; double* full_ref = ctx->tmp.p; double* work = ctx->Ap.p;
+    TRY(op_launch(ctx, ctx->u.p, local_ref, matrix_free, nullptr, false));
+    CU(cudaMemcpyAsync(full_ref, local_ref, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    TRY(dist_post_spmv(ctx, full_ref));
+    const double* ref = (what == 1) ? local_ref : full_ref;
+    i64 bad = 0;
     unsigned long long prev = 0, h[2];
     for (i64 k = 0; k < reps; k++) {
-        TRY(op_launch(ctx, ctx->u.p, ctx->Ap.p, matrix_free, nullptr, false));
-        TRY(dist_post_spmv(ctx, ctx->Ap.p));
-        LAUNCH(ctx, k_count_diff, vec_grid(n), VEC_THREADS, 0, (const double*)ctx->Ap.p, (const double*)ctx->tmp.p, n, cnt.p);
-        if ((k & 255) == 255 || k == reps - 1) {              // host check every 256 launches: counts the launches-with-a-fault to within a batch
+        if (what & 1) TRY(op_launch(ctx, ctx->u.p, work, matrix_free, nullptr, false));
+        else CU(cudaMemcpyAsync(work, local_ref, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (what & 2) TRY(dist_post_spmv(ctx, work));
+        LAUNCH(ctx, k_count_diff, vec_grid(n), VEC_THREADS, 0, (const double*)work, ref, n, cnt.p);
+        if ((k & 255) == 255 || k == reps - 1) {              // host check every 256 applications
             CU(cudaMemcpyAsync(h, cnt.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
-            if (h[0] != prev) { bad_reps++; prev = h[0]; }
+            if (h[0] != prev) { bad++; prev = h[0]; }
         }
     }
-    if (mismatching_reps) *mismatching_reps = bad_reps;
+    if (mismatching_batches) *mismatching_batches = bad;
     if (mismatching_entries) *mismatching_entries = (i64)prev;
+    return TOE_OK;
+}
+
+int cg_trace(toe_ctx* ctx, double* out, i64 iterations) {
+    if (!ctx->cg_trace.p) return toe_fail(ctx, TOE_ERR_STATE, "no CG trace: set TOE_CG_TRACE=1 before a partitioned solve");
+    if (iterations > HIST_CAP) iterations = HIST_CAP;
+    CU(cudaMemcpy(out, ctx->cg_trace.p, 4 * (size_t)iterations * sizeof(double), cudaMemcpyDeviceToHost));
     return TOE_OK;
 }
 
