@@ -391,9 +391,10 @@ def run_b200(args, pkg, prog):
         u = ctx.solution()
         return st_, e_, c_, u
 
-    e2e_step("e2e warm-up")                               # allocations are reused afterwards
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 3)      # bounded: the e2e arm repeats the full path incl. set-up
+    if not args.no_e2e_warmup:
+        e2e_step("e2e warm-up")                           # allocations are reused afterwards
     tm_setup = ctx.timings()
-    e2e_steps = min(args.steps, 3)                        # bounded: the e2e arm repeats the full path incl. set-up
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
@@ -511,6 +512,8 @@ def main():
     ap.add_argument("--matrix-free", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-two-level", action="store_true", help="skip the extra two-level-preconditioner solve reported in stages")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="timed end-to-end steps (default min(steps, 3))")
+    ap.add_argument("--no-e2e-warmup", action="store_true", help="skip the untimed end-to-end step (long workloads)")
     ap.add_argument("--deadline", type=float, default=float(os.environ.get("TOE_BENCH_DEADLINE", "780")),
                     help="seconds after which the run ends with an error line instead of hanging")
     args = ap.parse_args()

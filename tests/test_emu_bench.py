@@ -14,7 +14,7 @@ import emu_support  # noqa: E402
 
 
 def _args(**kw):
-    d = dict(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=False, no_cpu_baseline=True, no_two_level=False, deadline=600.0)
+    d = dict(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=False, no_cpu_baseline=True, no_two_level=False, deadline=600.0, e2e_steps=None, no_e2e_warmup=False)
     d.update(kw)
     return types.SimpleNamespace(**d)
 

@@ -466,7 +466,10 @@ def get_face_nodes(cell):
 DIRECT_EQUIVALENT_TOL = 1e-10
 
 
-def _solve(dh, constraints, tol, itmax, matrix_free, verbose, history=False, two_level=False):
+def _solve(dh, constraints, tol, itmax, matrix_free, verbose, history=False, two_level=False, stress_material=None):
+    """`stress_material`: keyword arguments of Context.calculate_stresses built from the CALLER's material arguments — the reference
+    passes λ, μ (or material_model, density_data) of the solve call to calculate_stresses (FiniteElementAnalysis.jl:553 / :854), which
+    may legally differ from what K was assembled with."""
     ctx = dh.ctx
     for ch in constraints:                              # SINGLE APPLICATION POINT (:540-542)
         ctx.apply_dirichlet(ch.prescribed_dofs)
@@ -479,33 +482,51 @@ def _solve(dh, constraints, tol, itmax, matrix_free, verbose, history=False, two
         print("WARNING: PCG did not converge in %d iterations (residual %.3e)" % (st["niter"], st["res_M"]))
     u = ctx.solution()
     energy, _compliance, _ = ctx.energy()
-    _, _, max_vm, max_cell = ctx.stresses(False, False)
+    if stress_material:
+        _, _, max_vm, max_cell = ctx.calculate_stresses(None, **stress_material)
+        sf = StressField(ctx, lambda: ctx.calculate_stresses(u, want_sigma=True, want_vm=True, **stress_material))
+    else:
+        _, _, max_vm, max_cell = ctx.stresses(False, False)
+        sf = StressField(ctx)
     if verbose:
         print("Analysis complete")
         print("Deformation energy: %r J" % energy)
         print("Maximum von Mises stress: %r at cell %d" % (max_vm, max_cell))
     dh.last_stats = st
-    return u, energy, StressField(ctx), max_vm, max_cell
+    return u, energy, sf, max_vm, max_cell
+
+
+def _direct_itmax(dh):
+    return max(100000, 4 * dh.ctx.ndofs)
 
 
 def solve_system(K, f, dh, cellvalues, lam, mu, *constraints):
-    return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ctx.ndofs), False, True)
+    return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, _direct_itmax(dh), False, True, stress_material={"lame": (lam, mu)})
 
 
 def solve_system_simp(K, f, dh, cellvalues, material_model, density_data, *constraints):
-    return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ctx.ndofs), False, True)
+    return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, _direct_itmax(dh), False, True,
+                  stress_material=_material_kwargs(material_model, density_data, dh.ctx.ne))
+
+
+def _robust(dh, constraints, config, stress_material):
+    config = config or SolverConfig()
+    tl = config.preconditioner == "two_level"
+    # :direct, and :auto below 50 000 DOFs (select_solver_method, RobustSolver.jl:206, picks the factorisation there): the GPU path
+    # has no factorisation, so PCG runs to the accuracy a direct solve delivers
+    if config.method == "direct" or (config.method == "auto" and dh.ctx.ndofs < 50000):
+        return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, _direct_itmax(dh), config.matrix_free, config.verbose, two_level=tl,
+                      stress_material=stress_material)
+    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, config.history, two_level=tl,
+                  stress_material=stress_material)
 
 
 def solve_system_robust(K, f, dh, cellvalues, lam, mu, *constraints, config: SolverConfig | None = None):
-    config = config or SolverConfig()
-    tl = config.preconditioner == "two_level"
-    if config.method == "direct":
-        return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ctx.ndofs), config.matrix_free, config.verbose, two_level=tl)
-    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, config.history, two_level=tl)
+    return _robust(dh, constraints, config, {"lame": (lam, mu)})
 
 
 def solve_system_robust_simp(K, f, dh, cellvalues, material_model, density_data, *constraints, config: SolverConfig | None = None):
-    return solve_system_robust(K, f, dh, cellvalues, None, None, *constraints, config=config)
+    return _robust(dh, constraints, config, _material_kwargs(material_model, density_data, dh.ctx.ne))
 
 
 def solve_system_adaptive(K, f, dh, cellvalues, lam, mu, *constraints):

@@ -30,7 +30,8 @@ __global__ void k_scan_tile_sums(const int* __restrict__ in, int* __restrict__ s
 }
 
 // scans one tile; thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile
-__global__ void k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ tile_offsets, i64 n) {
+// `in` and `out` may be the same array (every thread reads its own items before it writes them): no __restrict__ on the two
+__global__ void k_scan_tiles(const int* in, int* out, const int* __restrict__ tile_offsets, i64 n) {
     __shared__ int sh[SCAN_THREADS / 32];
     i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
@@ -49,6 +50,14 @@ __global__ void k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, 
     for (int k = 0; k < SCAN_ITEMS; k++) { i64 i = base + k; if (i < n) out[i] = run; run += v[k]; }
 }
 
+// 64-bit total of a non-negative int array: the 32-bit scan below is only valid if this fits an int
+__global__ void k_total_i64(const int* __restrict__ in, i64 n, unsigned long long* out) {
+    unsigned long long s = 0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) s += (unsigned long long)(unsigned int)in[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
 __global__ void k_write_total(const int* __restrict__ in_last, const int* __restrict__ out_last_excl, int* out_total, int have) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *out_total = have ? (*out_last_excl + *in_last) : 0;
 }
@@ -58,6 +67,15 @@ __global__ void k_write_total(const int* __restrict__ in_last, const int* __rest
 int scan_exclusive_i32(toe_ctx* ctx, const int* in, int* out, i64 n, i64* total_out) {
     if (n == 0) { CU(cudaMemsetAsync(out, 0, sizeof(int), ctx->stream)); if (total_out) *total_out = 0; return TOE_OK; }
     i64 ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    {   // overflow guard: the prefix sums are 32-bit, so the total must fit (checked in 64 bits BEFORE scanning; in may alias out)
+        DevBuf<unsigned long long> tot64; CU(tot64.alloc(1));
+        CU(cudaMemsetAsync(tot64.p, 0, sizeof(unsigned long long), ctx->stream));
+        LAUNCH(ctx, k_total_i64, min_u(div_up(n, 256), 2048u), 256, 0, in, n, tot64.p);
+        unsigned long long h = 0;
+        CU(cudaMemcpyAsync(&h, tot64.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (h > 2147483647ULL) return toe_fail(ctx, TOE_ERR_MESH, "index overflow: a prefix sum would reach %llu > 2^31-1", h);
+    }
     // keep the last input element: aliasing would overwrite it before k_write_total reads it
     DevBuf<int> last_in; CU(last_in.alloc(1));
     CU(cudaMemcpyAsync(last_in.p, in + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -68,7 +86,6 @@ int scan_exclusive_i32(toe_ctx* ctx, const int* in, int* out, i64 n, i64* total_
         LAUNCH(ctx, k_scan_tile_sums, (unsigned)ntiles, SCAN_THREADS, 0, in, sums.p, n);
         i64 dummy;
         TRY(scan_exclusive_i32(ctx, sums.p, sums.p, ntiles, &dummy));
-        if (dummy > 2147483647LL) return toe_fail(ctx, TOE_ERR_MESH, "index overflow: a prefix sum exceeds 2^31-1 (%lld)", dummy);
         LAUNCH(ctx, k_scan_tiles, (unsigned)ntiles, SCAN_THREADS, 0, in, out, (const int*)sums.p, n);
         CU(cudaStreamSynchronize(ctx->stream));   // sums goes out of scope
     }

@@ -150,7 +150,7 @@ function setup_problem(grid::Grid, interpolation_order::Int = 1; device::Integer
     nfd = Vector{Int}(undef, nn)
     check(ctx, ccall((:toe_get_node_dofs, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), ctx.ptr, nfd))
     dh = B200DofHandler(ctx, grid, nd[], nfd)
-    GRID_CTX[objectid(grid)] = ctx                                          # boundary-node selection on this grid reuses the device mesh
+    GRID_CTX[grid] = ctx                                          # boundary-node selection on this grid reuses the device mesh
     return dh, B200CellValues(npc, npc == 4 ? 4 : 8), B200Matrix(ctx, nd[], nnz[]), B200Vector(ctx, nd[])
 end
 
@@ -292,7 +292,10 @@ end
 
 const DIRECT_EQUIVALENT_TOL = 1e-10      # `K \ f` entry points run PCG to the accuracy the reference's direct solve reaches
 
-function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbose, two_level = false)
+# `stress` = closure u -> (stress_field, max_von_mises, max_stress_cell) built from the CALLER's material arguments: the reference hands
+# λ, μ (or material_model, density_data) of the solve call to calculate_stresses (FiniteElementAnalysis.jl:553 / :854), and they may
+# legally differ from what K was assembled with
+function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbose, two_level, stress)
     c = dh.ctx
     for ch in constraints                                  # SINGLE APPLICATION POINT (:540-542)
         m = Ref(0.0)
@@ -308,27 +311,33 @@ function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbos
     check(c, ccall((:toe_get_solution, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), c.ptr, u))
     e = Ref(0.0); comp = Ref(0.0)
     check(c, ccall((:toe_energy, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}, Ptr{Float64}), c.ptr, e, comp, C_NULL))
-    mx = Ref(0.0); arg = Ref{Int64}(0)
-    check(c, ccall((:toe_stresses, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}), c.ptr, C_NULL, C_NULL, mx, arg))
+    sf, mx, arg = stress(u)
     if verbose
         println("Analysis complete"); println("Deformation energy: $(e[]) J")
-        println("Maximum von Mises stress: $(mx[]) at cell $(arg[])")
+        println("Maximum von Mises stress: $(mx) at cell $(arg)")
     end
-    ne = getncells(dh.grid)
-    return u, e[], StressField(c, ne, length(dh.grid.cells[1].nodes) == 4 ? 4 : 8, nothing), mx[], Int(arg[])
+    return u, e[], sf, mx, arg
 end
+_direct_itmax(dh) = max(100000, 4 * dh.ndofs)
 
-solve_system(K, f, dh, cv, λ, μ, constraints...) = _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ndofs), false, true)
-solve_system_simp(K, f, dh, cv, material_model, density_data, constraints...) = _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ndofs), false, true)
-function solve_system_robust(K, f, dh, cv, λ, μ, constraints...; config::SolverConfig = SolverConfig())
+solve_system(K, f, dh, cv, λ, μ, constraints...) =
+    _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, _direct_itmax(dh), false, true, false, u -> calculate_stresses(u, dh, cv, λ, μ))
+solve_system_simp(K, f, dh, cv, material_model, density_data, constraints...) =
+    _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, _direct_itmax(dh), false, true, false, u -> calculate_stresses_simp(u, dh, cv, material_model, density_data))
+function _robust(dh, constraints, config::SolverConfig, stress)
     config.method in (:auto, :cg, :direct) || error("method :$(config.method) is not on the GPU path (SPD system: :cg only)")
     config.preconditioner in (:diagonal, :two_level) || error("preconditioner :$(config.preconditioner) is not on the GPU path (:diagonal or :two_level)")
     tl = config.preconditioner == :two_level             # Jacobi + rigid-body coarse space (TOE_PCG_TWO_LEVEL)
-    config.method == :direct && return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, max(100000, 4 * dh.ndofs), config.matrix_free, config.verbose, tl)
-    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, tl)
+    # :direct, and :auto below 50 000 DOFs (select_solver_method, RobustSolver.jl:206, picks the factorisation there): no factorisation on
+    # the GPU path, so PCG runs to the accuracy a direct solve delivers
+    (config.method == :direct || (config.method == :auto && dh.ndofs < 50000)) &&
+        return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, _direct_itmax(dh), config.matrix_free, config.verbose, tl, stress)
+    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, tl, stress)
 end
+solve_system_robust(K, f, dh, cv, λ, μ, constraints...; config::SolverConfig = SolverConfig()) =
+    _robust(dh, constraints, config, u -> calculate_stresses(u, dh, cv, λ, μ))
 solve_system_robust_simp(K, f, dh, cv, material_model, density_data, constraints...; config::SolverConfig = SolverConfig()) =
-    solve_system_robust(K, f, dh, cv, nothing, nothing, constraints...; config = config)
+    _robust(dh, constraints, config, u -> calculate_stresses_simp(u, dh, cv, material_model, density_data))
 function solve_system_adaptive(K, f, dh, cv, λ, μ, constraints...)
     n = dh.ndofs
     n < 50000 && return solve_system(K, f, dh, cv, λ, μ, constraints...)                     # :574-575
@@ -339,9 +348,11 @@ end
 # ---- boundary-node selection (SelectNodesForBC.jl) and surface traction (SurfaceTraction.jl) ----------------------------------
 # The reference caches the surface nodes per grid (GRID_CACHE_STORAGE, SelectNodesForBC.jl:271-301); here the ctx that holds the
 # grid's mesh is remembered per grid object (set by setup_problem).
-const GRID_CTX = Dict{UInt,Ctx}()
+# Weak keys: the entry (and with it the ctx — mesh, pattern, K in HBM — once its dof handler is gone too) disappears with the grid; a grid
+# that is set up again replaces its entry, and the replaced ctx is released by its finalizer (toe_destroy).
+const GRID_CTX = WeakKeyDict{Grid,Ctx}()
 function _grid_ctx(grid::Grid)
-    haskey(GRID_CTX, objectid(grid)) && return GRID_CTX[objectid(grid)]
+    haskey(GRID_CTX, grid) && return GRID_CTX[grid]
     dh, _, _, _ = setup_problem(grid)
     return dh.ctx
 end
