@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
     if (done_flag && *done_flag) return;
     const int tid = threadIdx.x;
     if (tid == 0) {
-        for (int s = 0; s < SPMV_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + SPMV_STAGES + s), 1); }
+        // full[s]: one arrival (the producer's expect_tx) + the bytes; empty[s]: one arrival per consumer GROUP — see the consumer loop
+        for (int s = 0; s < SPMV_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + SPMV_STAGES + s), SPMV_GROUPS); }
     }
     __syncthreads();
     const int nchunks = (nq + R - 1) / R;
@@ -130,10 +131,21 @@ __global__ void __launch_bounds__(SPMV_PTHREADS, 1) k_spmv_bsr_pipe(const int* _
         const int group = tid / SPMV_CONS, gt = tid - group * SPMV_CONS;
         const int lr = gt / 3, c = gt - 3 * lr;
         int i = 0;
+        // Every consumer group is a consumer of EVERY fill of every stage: the chunks it does not process it still waits for and
+        // releases (one thread).  A parity wait means "the phase of this parity has completed", which is also true of the phase BEFORE
+        // the one the waiter means while that one is still in flight — so a waiter may never be more than one phase away from the
+        // barrier.  With the groups taking alternate chunks, the fill of a stage before a group's own was the OTHER group's; waiting for
+        // lap L+1 without having seen lap L complete let the wait pass on lap L-1 whenever the copies of two consecutive chunks landed
+        // more than a chunk's processing time out of order (≈2 in 10^6 launches at 10M tets: stale rows in y, a wrong p'Ap — the
+        // round-1 "transient CG breakdown", and an illegal address when the stage still held no data at all).  The refill of a stage
+        // needs the release of both groups, so no wait can be overtaken by two fills either.
         for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, i++) {
-            if ((i % SPMV_GROUPS) != group) continue;
             const int st = i % SPMV_STAGES;
             const unsigned ph = (unsigned)(i / SPMV_STAGES) & 1u;
+            if ((i % SPMV_GROUPS) != group) {
+                if (gt == 0) { mbar_wait(smem_u32(bars + st), ph); mbar_arrive(smem_u32(bars + SPMV_STAGES + st)); }
+                continue;
+            }
             const int r0 = chunk * R, r1 = min(r0 + R, nq);
             const int s0 = __ldg(&blk_ptr[r0]), s1 = __ldg(&blk_ptr[r1]);
             const bool has_row = (lr < r1 - r0) && (gt < 3 * R);
