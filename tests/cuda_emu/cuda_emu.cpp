@@ -86,6 +86,11 @@ struct Rank {                      // per OS thread (= per emulated GPU / ctx dr
     cudaError_t last_error = cudaSuccess;
     size_t stack_bytes = 0;
     bool deadlock = false;
+    // EMU_BULK_DELAY: bulk async copies complete late and out of order (see emu::bulk_g2s)
+    struct PendingCopy { void* dst; const void* src; unsigned bytes; void* bar; unsigned long long due; };
+    std::vector<PendingCopy> pending;
+    unsigned long long pass = 0, fill_rng = 0x2545F4914F6CDD1DULL;
+    void* last_fill_bar = nullptr; unsigned long long last_fill_pass = ~0ULL, last_fill_delay = 0;
 };
 thread_local Rank* g_rank = nullptr;
 
@@ -165,6 +170,22 @@ void run_grid_coresident(Rank& r, unsigned grid, unsigned T) {
     r.bs = &r.bs0;
 }
 
+// bulk async copies whose (emulated) completion time has come: data lands, the transaction bytes are taken off the barrier
+void deliver_due_copies(Rank& r, bool all) {
+    for (size_t k = 0; k < r.pending.size();) {
+        Rank::PendingCopy& c = r.pending[k];
+        if (!all && c.due > r.pass) { k++; continue; }
+        memcpy(c.dst, c.src, c.bytes);
+        unsigned long long* b = (unsigned long long*)c.bar;
+        unsigned ph = (unsigned)(*b & 1); int cnt = (int)((*b >> 1) & 0xfff), pend = (int)((*b >> 13) & 0xfff); long long tx = (long long)(int)(*b >> 32);
+        tx -= c.bytes;
+        *b = (unsigned long long)(ph & 1) | ((unsigned long long)(cnt & 0xfff) << 1) | ((unsigned long long)(pend & 0xfff) << 13) | ((unsigned long long)(unsigned)(int)tx << 32);
+        if (pend == 0 && tx == 0) *b = (unsigned long long)((ph ^ 1u) & 1) | ((unsigned long long)(cnt & 0xfff) << 1) | ((unsigned long long)(cnt & 0xfff) << 13);
+        r.progress++;
+        r.pending[k] = r.pending.back(); r.pending.pop_back();
+    }
+}
+
 void run_block(Rank& r, unsigned b, unsigned T, size_t smem) {
     blockIdx.x = b;
     BlockState& bs = r.bs0;
@@ -182,6 +203,8 @@ void run_block(Rank& r, unsigned b, unsigned T, size_t smem) {
     if (shuffle_env) { if (!rng) rng = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)atoll(shuffle_env); order.resize(T); for (unsigned t = 0; t < T; t++) order[t] = t; }
     while (remaining > 0) {
         unsigned long long p0 = r.progress;
+        r.pass++;
+        deliver_due_copies(r, false);
         if (shuffle_env)
             for (unsigned t = T; t > 1; t--) { rng = rng * 6364136223846793005ULL + 1442695040888963407ULL; unsigned j = (unsigned)((rng >> 33) % t); std::swap(order[t - 1], order[j]); }
         for (unsigned tt = 0; tt < T; tt++) {
@@ -200,6 +223,11 @@ void run_block(Rank& r, unsigned b, unsigned T, size_t smem) {
                 return;
             }
         } else idle_passes = 0;
+    }
+    if (!r.pending.empty()) {                              // a block must have waited for every copy it issued
+        fprintf(stderr, "cuda_emu: block %u ended with %zu bulk copies in flight\n", b, r.pending.size());
+        r.last_error = 719;
+        r.pending.clear();
     }
 }
 
@@ -359,6 +387,21 @@ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
     if ((bytes & 15) || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) {
         fprintf(stderr, "cuda_emu: cp.async.bulk with unaligned operands (dst %p src %p bytes %u)\n", dst, src, bytes);
         g_rank->last_error = 716;
+    }
+    // EMU_BULK_DELAY=<passes>: the copies of one fill (same barrier, issued in the same scheduler pass) complete together but LATE —
+    // after 0 or <passes> scheduler passes, pseudo-randomly per fill — so the fills of consecutive stages land out of order, as they
+    // may on hardware.  A pipeline protocol whose waits can be satisfied by the wrong phase then reads a stage before its data is there.
+    const char* delay_s = getenv("EMU_BULK_DELAY");
+    const long long delay_env = delay_s ? atoll(delay_s) : 0;
+    Rank& r = *g_rank;
+    if (delay_env > 0 && r.bs == &r.bs0) {
+        if (r.last_fill_bar != bar || r.last_fill_pass != r.pass) {
+            r.fill_rng = r.fill_rng * 6364136223846793005ULL + 1442695040888963407ULL;
+            r.last_fill_delay = ((r.fill_rng >> 40) % 3 == 0) ? (unsigned long long)delay_env : 0ULL;
+            r.last_fill_bar = bar; r.last_fill_pass = r.pass;
+        }
+        r.pending.push_back({dst, src, bytes, bar, r.pass + 1 + r.last_fill_delay});
+        return;
     }
     memcpy(dst, src, bytes);
     unsigned long long* b = (unsigned long long*)bar;

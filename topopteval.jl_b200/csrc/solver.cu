@@ -315,6 +315,7 @@ static int op_launch(toe_ctx* ctx, const double* x, double* y, int matrix_free, 
         if (R > SPMV_ROWS) R = SPMV_ROWS;
         int nchunks = (ctx->nq + R - 1) / R;
         unsigned grid = (unsigned)(nchunks < N_SM ? nchunks : N_SM);          // persistent: one CTA per SM
+        if (const char* eg = getenv("TOE_SPMV_GRID")) { int v = atoi(eg); if (v >= 1 && (unsigned)v < grid) grid = (unsigned)v; }   // tests: many chunks per CTA on small meshes
         if (!ctx->spmv_attr_set) {
             CU(cudaFuncSetAttribute(k_spmv_bsr_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_PSMEM));
             CU(cudaFuncSetAttribute(k_spmv_bsr_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SPMV_PSMEM));
