@@ -104,12 +104,12 @@ static int exchange_allgather(toe_ctx* ctx, double* y, double* scal, int count);
 bool dist_active(toe_ctx* ctx) { return ctx->dist != nullptr; }
 
 // Transport of the per-iteration exchange (read at every set-up):
-//   allgather (default)  ONE ncclAllGather carries every rank's packed interface values and its partial scalars
-//   sendrecv             grouped ncclSend/ncclRecv per neighbour + ncclAllReduce of the scalars.  NOT the default: at 10M tets / N=2 on this
-//                        stack (NCCL 2.28.9, B200, one process per GPU) roughly one solve in ten met a transient fault in mid-iteration
-//                        (identical state fingerprints before the solve, residual history leaving the reference run at iteration ~7500,
-//                        bit-identical on both ranks; 3 of 29 solves, against 0 of 36 on the two other transports — profiles/r2_dist_diagnosis.md)
-//   p2p                  fused peer-memory kernel over CUDA IPC mailboxes (also TOE_DIST_P2P=1)
+//   allgather (default)  ONE ncclAllGather carries every rank's packed interface values and its partial scalars: one collective and
+//                        3 launches per exchange (3.11 s per 10M-tet solve at N=2 against 3.24 s for send/recv + allreduce)
+//   sendrecv             grouped ncclSend/ncclRecv per neighbour + ncclAllReduce of the scalars (TOE_DIST_XCHG=sendrecv)
+//   p2p                  fused peer-memory kernel over CUDA IPC mailboxes (TOE_DIST_XCHG=p2p or TOE_DIST_P2P=1)
+// All three do the same arithmetic in the same order (bit-identical iterates).  The transient CG faults of round 1 were NOT a transport
+// problem: they came from the SpMV's pipeline protocol (profiles/r2_dist_diagnosis.md); 48 of 48 solves are clean on either NCCL transport.
 enum XchgMode { XCHG_ALLGATHER = 0, XCHG_SENDRECV = 1, XCHG_P2P = 2 };
 static XchgMode xchg_mode() {
     const char* m = getenv("TOE_DIST_XCHG");
