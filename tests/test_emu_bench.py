@@ -14,7 +14,7 @@ import emu_support  # noqa: E402
 
 
 def _args(**kw):
-    d = dict(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=False, no_cpu_baseline=True, no_two_level=False, deadline=600.0, e2e_steps=None, no_e2e_warmup=False)
+    d = dict(gpus=1, steps=2, warmup=1, impl="b200", workload="toy", matrix_free=False, no_cpu_baseline=True, no_two_level=False, deadline=600.0, e2e_steps=None, no_e2e_warmup=False, no_l2=False)
     d.update(kw)
     return types.SimpleNamespace(**d)
 
@@ -59,6 +59,8 @@ def test_bench_b200_arm_contract_on_emulated_build(monkeypatch, mf):
     assert mp["elements_assembled_per_s"] is None or mp["elements_assembled_per_s"] > 0
     assert mp["pcg_seconds_to_1e-8"] > 0 and mp["pcg_iterations"] > 0
     assert d["stages"]["pcg_converged"] and d["stages"]["pcg_iterations_per_step"] == [mp["pcg_iterations"]] * 2 and d["stages"]["energy"] > 0
+    l2 = d["stages"]["l2_criterion"]
+    assert l2["converged"] and l2["pcg_iterations"] != mp["pcg_iterations"] and l2["rel_res_l2"] < 1e-7
     tl = d["stages"]["two_level_preconditioner"]
     assert (mf and tl is None) or "error" not in tl and tl["converged"] and tl["pcg_iterations"] < mp["pcg_iterations"] and tl["energy_rel_diff_vs_jacobi"] < 1e-6
 

@@ -331,6 +331,46 @@ def test_pcg_krylov_semantics_and_iteration_count(ctx, pkg, golden_c1):
     assert st3["niter"] == st["niter"]
 
 
+def test_l2_norm_criterion_and_true_residual(ctx, pkg, fo, golden_syn):
+    """TOE_PCG_L2_NORM (SURVEY §8(b) norm_kind): stop on ||r||_2 <= atol + rtol*||r0||_2 instead of Krylov.jl's M-norm rule, on the
+    24x8x4 synthetic cantilever, assembled and matrix-free; checked against an l2-stopped PCG of the oracle's K (same recurrence in
+    numpy) and against the true residual the library recomputes after the solve (toe_pcg_stats.true_res)."""
+    mg = pkg.meshgen
+    pts, cells = mg.cantilever(24, 8, 4)
+    _setup(ctx, pts, cells)
+    lam, mu = fo.create_material_model(1.0, 0.3)
+    prob = fo.setup_problem(pts, cells)
+    fo.assemble_stiffness_matrix(prob, lam, mu)
+    load = mg.nodes_at_plane(pts, 0, 60.0); fixed = mg.nodes_at_plane(pts, 0, 0.0)
+    fo.apply_force(prob, load, [0.0, 0.0, -1.0])
+    pres = fo.fixed_boundary_dofs(prob, fixed)
+    fo.apply_dirichlet(prob, pres)
+    K = prob.K().tocsr(); f = prob.f.copy()
+    # numpy PCG with the l2 rule (Jacobi, x0 = 0)
+    Minv = 1.0 / np.where(np.abs(K.diagonal()) < 1e-12, 1.0, K.diagonal())
+    x = np.zeros_like(f); r = f.copy(); z = Minv * r; p = z.copy(); gamma = r @ z
+    eps = 1e-9 + 1e-9 * np.linalg.norm(r); it_ref = 0
+    while np.linalg.norm(r) > eps and it_ref < 100000:
+        Ap = K @ p; alpha = gamma / (p @ Ap); x += alpha * p; r -= alpha * Ap; z = Minv * r; g2 = r @ z; p = z + (g2 / gamma) * p; gamma = g2; it_ref += 1
+    for mf in (False, True):
+        (ctx.set_material_lame if mf else ctx.assemble_lame)(lam, mu)
+        ctx.add_nodal_force(load, [0.0, 0.0, -1.0]); ctx.apply_dirichlet(pres)
+        st_m = ctx.solve_pcg(1e-9, 1e-9, 100000, matrix_free=mf)
+        st = ctx.solve_pcg(1e-9, 1e-9, 100000, matrix_free=mf, l2_norm=True, history=True)
+        assert st["converged"] == 1 and st_m["converged"] == 1
+        assert abs(st["niter"] - it_ref) <= max(5, it_ref // 50), (mf, st["niter"], it_ref)          # l2 rule: the oracle's count
+        assert st["niter"] != st_m["niter"]                                                            # and not the M-norm one
+        nf = np.linalg.norm(f)
+        assert abs(st["res0_M"] - nf) <= 1e-12 * nf and st["res_M"] <= 1e-9 + 1e-9 * nf                # history / stats hold l2 norms
+        assert st["residuals"][0] == st["res0_M"] and st["residuals"][-1] == st["res_M"]
+        # the recomputed true residual agrees with the recurrence to rounding, in the norm of the test
+        assert st["true_res"] <= 2.0 * (1e-9 + 1e-9 * nf) and abs(st["rel_res_l2"] - st["true_res"] / nf) <= 1e-12
+        assert st_m["true_res"] <= 2.0 * (1e-9 + 1e-9 * st_m["res0_M"])                                # M-norm run: true_res in the M-norm
+        assert rel(ctx.solution(), x) <= 1e-7
+    with pytest.raises(pkg.TopOptError):
+        ctx.solve_pcg(1e-9, 1e-9, 100, two_level=True, l2_norm=True)                                   # Jacobi only
+
+
 @pytest.mark.parametrize("load", ["tip", "volume"])
 @pytest.mark.parametrize("matrix_free", [False, True])
 def test_solve_c2_hex_simp(ctx, pkg, golden_c2, load, matrix_free):
