@@ -49,6 +49,7 @@ static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y =
 struct alignas(16) double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 // ---- runtime API (subset) --------------------------------------------------------------------------------------------
 typedef int cudaError_t;
@@ -61,7 +62,8 @@ typedef struct emu_graph* cudaGraphExec_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaStreamNonBlocking = 1 };
 enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
-enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+enum { cudaSharedmemCarveoutMaxShared = 100 };
 enum { cudaIpcMemLazyEnablePeerAccess = 1 };
 struct cudaIpcMemHandle_t { char reserved[64]; };
 struct cudaDeviceProp { char name[256]; int major, minor; int multiProcessorCount; };

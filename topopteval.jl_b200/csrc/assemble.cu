@@ -289,15 +289,16 @@ __device__ __forceinline__ void block_acc(const double ga[3], const double gb[3]
 }
 
 template <int G>
-__global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __restrict__ inc_ptr, const int* __restrict__ inc,
+__global__ void __launch_bounds__(ASM_ROWS_THREADS, G <= 32 ? 5 : 4) k_asm_rows_tet(const int* __restrict__ inc_ptr, const int* __restrict__ inc,
                                                                    const int* __restrict__ blk_ptr, const int* __restrict__ blk_col,
                                                                    const int* __restrict__ ctr_ptr, const unsigned short* __restrict__ rctr,
                                                                    const int* __restrict__ cq, const double* __restrict__ xq, Material mat,
                                                                    double* __restrict__ val, i64 ldv, int nq, int* err) {
     constexpr int ROWS = ASM_ROWS_THREADS / G;
     constexpr bool IN_WARP = (G <= 32);            // the group is (part of) one warp: warp-level synchronisation suffices
+    constexpr int CPL = ASM_CH / G > 0 ? ASM_CH / G : 1;      // cells per lane and pass (2 for G = 16, 1 otherwise)
     __shared__ double geo[ROWS][ASM_GEO][ASM_CH];
-    __shared__ double dpart[ASM_ROWS_THREADS][6];  // per-thread partial of the row's diagonal block (upper triangle)
+    __shared__ double dpart[IN_WARP ? 1 : ASM_ROWS_THREADS][6];      // G = 64 only: per-thread partials of the row's diagonal block
     __shared__ int s_maxcells;
     const int rl = threadIdx.x / G, lane = threadIdx.x - rl * G;
     const int row = blockIdx.x * ROWS + rl;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __
         const int b0 = __ldg(&blk_ptr[row]), b1 = __ldg(&blk_ptr[row + 1]);
         if (lane < b1 - b0) { s = b0 + lane; col = __ldg(&blk_col[s]); ci = __ldg(&ctr_ptr[s]); chi = __ldg(&ctr_ptr[s + 1]); }
     }
-    int ncell = i_hi - i_lo;
+    const int ncell = i_hi - i_lo;
     int npass;
     if (IN_WARP) {                                  // uniform over the warp (it may hold two or more rows)
         int m = ncell;
@@ -323,20 +324,30 @@ __global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __
         npass = (s_maxcells + ASM_CH - 1) / ASM_CH;
     }
     const bool is_diag = (s >= 0 && col == row);
-    double acc[9], dacc[9];
+    double acc[9], dacc[6];                         // dacc: upper triangle of the diagonal block (00 01 02 11 12 22)
 #pragma unroll
-    for (int k = 0; k < 9; k++) { acc[k] = 0.0; dacc[k] = 0.0; }
+    for (int k = 0; k < 9; k++) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) dacc[k] = 0.0;
     unsigned ent = (ci < chi) ? (unsigned)__ldg(&rctr[ci]) : 0u;          // next contribution of this thread's block
     for (int pass = 0; pass < npass; pass++) {
         const int k0 = pass * ASM_CH;
         int cnt = ncell - k0;
         cnt = cnt < 0 ? 0 : (cnt > ASM_CH ? ASM_CH : cnt);
-        for (int k = lane; k < cnt; k += G) {
-            const int ea = __ldg(&inc[i_lo + k0 + k]);
-            const int e = ea >> 2;
+        // the incidence entries and connectivities of all this lane's cells are requested before any geometry is evaluated: the
+        // chain incidence → connectivity → coordinates is paid once per pass, not once per cell
+        int ea[CPL]; int4 cn[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; j++) { const int k = lane + j * G; ea[j] = k < cnt ? __ldg(&inc[i_lo + k0 + k]) : -1; }
+#pragma unroll
+        for (int j = 0; j < CPL; j++) cn[j] = ea[j] >= 0 ? __ldg(reinterpret_cast<const int4*>(cq) + (ea[j] >> 2)) : make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < CPL; j++) {
+            if (ea[j] < 0) continue;
+            const int k = lane + j * G, e = ea[j] >> 2;
             double lam, mu; material_at(mat, e, lam, mu);
-            int q[4]; double X[4][3], g[4][3];
-            tet_load(cq, xq, e, q, X);
+            double X[4][3], g[4][3];
+            load3(xq, cn[j].x, X[0]); load3(xq, cn[j].y, X[1]); load3(xq, cn[j].z, X[2]); load3(xq, cn[j].w, X[3]);
             const double det = tet_grads(X, g);
             if (!(det > 0.0)) atomicMin(err + 1, e);
             const double w = det * (1.0 / 6.0);
@@ -347,10 +358,14 @@ __global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __
                 for (int i = 0; i < 3; i++) geo[rl][3 * a + i][k] = g[a][i];
             geo[rl][12][k] = wl; geo[rl][13][k] = wm;
             // the diagonal block has a contribution from every cell of the row (4x the work of an off-diagonal block): it is
-            // spread over the group here — each thread adds its cells (ascending), the partials are summed in lane order below
+            // spread over the group here — each thread adds its cells (ascending), the partials are summed in a fixed order below
             double ga[3];
-            sel4(g, ea & 3, ga);
-            block_acc(ga, ga, wl, wm, dacc);
+            sel4(g, ea[j] & 3, ga);
+            const double dot = (ga[0] * ga[0] + ga[1] * ga[1]) + ga[2] * ga[2];
+            const double wlm = wl + wm;
+            dacc[0] = fma(wlm, ga[0] * ga[0], fma(wm, dot, dacc[0])); dacc[1] = fma(wlm, ga[0] * ga[1], dacc[1]); dacc[2] = fma(wlm, ga[0] * ga[2], dacc[2]);
+            dacc[3] = fma(wlm, ga[1] * ga[1], fma(wm, dot, dacc[3])); dacc[4] = fma(wlm, ga[1] * ga[2], dacc[4]);
+            dacc[5] = fma(wlm, ga[2] * ga[2], fma(wm, dot, dacc[5]));
         }
         if (IN_WARP) __syncwarp(); else __syncthreads();
         if (!is_diag) {
@@ -369,18 +384,26 @@ __global__ void __launch_bounds__(ASM_ROWS_THREADS) k_asm_rows_tet(const int* __
         }
         if (IN_WARP) __syncwarp(); else __syncthreads();
     }
-    dpart[threadIdx.x][0] = dacc[0]; dpart[threadIdx.x][1] = dacc[1]; dpart[threadIdx.x][2] = dacc[2];
-    dpart[threadIdx.x][3] = dacc[4]; dpart[threadIdx.x][4] = dacc[5]; dpart[threadIdx.x][5] = dacc[8];
-    if (IN_WARP) __syncwarp(); else __syncthreads();
-    if (is_diag) {
-        double d[6] = {0, 0, 0, 0, 0, 0};
-        for (int l = 0; l < G; l++) {
-            const double* pp = dpart[rl * G + l];
+    // diagonal block = sum of the group's partials, in a fixed order: a butterfly over the lanes of the group (all lanes end up with
+    // the same bits), or — groups of two warps — through shared memory in lane order
+    if (IN_WARP) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) d[k] += pp[k];
+        for (int o = G / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 6; k++) dacc[k] += __shfl_xor_sync(0xffffffffu, dacc[k], o);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) dpart[threadIdx.x][k] = dacc[k];
+        __syncthreads();
+        if (is_diag) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) dacc[k] = 0.0;
+            for (int l = 0; l < G; l++)
+#pragma unroll
+                for (int k = 0; k < 6; k++) dacc[k] += dpart[rl * G + l][k];
         }
-        acc[0] = d[0]; acc[1] = d[1]; acc[2] = d[2]; acc[3] = d[1]; acc[4] = d[3]; acc[5] = d[4]; acc[6] = d[2]; acc[7] = d[4]; acc[8] = d[5];
     }
+    if (is_diag) { acc[0] = dacc[0]; acc[1] = dacc[1]; acc[2] = dacc[2]; acc[3] = dacc[1]; acc[4] = dacc[3]; acc[5] = dacc[4]; acc[6] = dacc[2]; acc[7] = dacc[4]; acc[8] = dacc[5]; }
     if (s >= 0) {
 #pragma unroll
         for (int k = 0; k < 9; k++) val[(size_t)k * ldv + s] = acc[k];
@@ -457,6 +480,11 @@ int assemble_current_material(toe_ctx* ctx, int variant) {
         CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
 #define ROWS_ARGS (const int*)ctx->inc_ptr.p, (const int*)ctx->inc.p, (const int*)ctx->blk_ptr.p, (const int*)ctx->blk_col.p, (const int*)ctx->ctr_ptr.p, \
         (const unsigned short*)ctx->rctr.p, (const int*)ctx->cq.p, (const double*)ctx->xq.p, amat, ctx->val.p, ldv, ctx->nq, ctx->errflag.p
+        if (!ctx->rows_attr_set) {                            // 5 CTAs x 29 KB per SM: ask for the large shared-memory carve-out
+            CU(cudaFuncSetAttribute(k_asm_rows_tet<16>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            CU(cudaFuncSetAttribute(k_asm_rows_tet<32>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            ctx->rows_attr_set = true;
+        }
         int gmin = 0;                                         // TOE_ASM_ROWS_G=32|64 forces a wider group (tests)
         if (const char* eg = getenv("TOE_ASM_ROWS_G")) gmin = atoi(eg);
         if (ctx->max_deg <= 16 && gmin <= 16)      LAUNCH(ctx, k_asm_rows_tet<16>, div_up(ctx->nq, ASM_ROWS_THREADS / 16), ASM_ROWS_THREADS, 0, ROWS_ARGS);

@@ -156,7 +156,7 @@ struct toe_ctx {
     CGScalars* cgs_host = nullptr;   // pinned readback buffer
 
     // cudaFuncSetAttribute is per device: the opt-in to large dynamic shared memory is remembered per ctx, not per process
-    bool spmv_attr_set = false;
+    bool spmv_attr_set = false, rows_attr_set = false;
     size_t ebe_attr_smem[2] = {0, 0}, pipe_attr_smem[2] = {0, 0};
 
     DistState* dist = nullptr;
