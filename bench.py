@@ -384,11 +384,18 @@ def run_b200(args, pkg, prog):
     sizes = ctx.local_sizes() if world > 1 else None
 
     # ---- end-to-end arm: host buffers in, u + energies out, every step ---------------------------------------
+    e2e_parts = {"set_mesh": [], "build_dofs": [], "build_pattern": [], "step": [], "solution_d2h": []}
+
     def e2e_step(tag):
         prog.at(tag + ": set-up")
-        setup()
-        st_, e_, c_ = step(tag)
-        u = ctx.solution()
+        t = [time.perf_counter()]
+        ctx.set_mesh(pts, cells, distributed=world > 1); t.append(time.perf_counter())
+        ctx.build_dofs(); t.append(time.perf_counter())
+        ctx.build_pattern(); t.append(time.perf_counter())
+        st_, e_, c_ = step(tag); t.append(time.perf_counter())
+        u = ctx.solution(); t.append(time.perf_counter())
+        for k, name in enumerate(("set_mesh", "build_dofs", "build_pattern", "step", "solution_d2h")):
+            e2e_parts[name].append(1e3 * (t[k + 1] - t[k]))
         return st_, e_, c_, u
 
     e2e_steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 3)      # bounded: the e2e arm repeats the full path incl. set-up
@@ -437,6 +444,7 @@ def run_b200(args, pkg, prog):
             "clocks": clocks,
             "e2e": {"value": ne_total * e2e_steps / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps, "pcg_iterations": int(st2["niter"]), "energy": e2,
+                    "host_wall_ms_per_call": {k: [round(x, 1) for x in v[-e2e_steps:]] for k, v in e2e_parts.items()},
                     "path": "host mesh (pinned) -> toe_set_mesh -> build_dofs -> build_pattern -> assemble -> loads -> apply! -> PCG -> energy -> u to host"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_ebe_tile+k_ebe_nodes" if mf else "k_spmv_bsr_pipe", "bound": "hbm", "achieved": spmv_bytes / spmv_s / 1e9, "peak": peaks["hbm_gbs"],

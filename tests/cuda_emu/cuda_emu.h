@@ -71,6 +71,13 @@ struct cudaDeviceProp { char name[256]; int major, minor; int multiProcessorCoun
 extern "C" {
 cudaError_t cudaMalloc(void** p, size_t bytes);
 cudaError_t cudaFree(void* p);
+// stream-ordered allocation: the emulated stream executes in program order, so these are the plain calls
+typedef struct emu_mempool* cudaMemPool_t;
+enum { cudaMemPoolAttrReleaseThreshold = 4 };
+static inline cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* pool, int) { *pool = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void*) { return cudaSuccess; }
 cudaError_t cudaMallocHost(void** p, size_t bytes);
 cudaError_t cudaFreeHost(void* p);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);

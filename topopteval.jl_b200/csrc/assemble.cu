@@ -549,7 +549,7 @@ int add_nodal_force(toe_ctx* ctx, const int64_t* nodes, i64 nnodes, const double
     if (nnodes <= 0 || !nodes) return toe_fail(ctx, TOE_ERR_ARG, "No nodes provided for force application.");   // :393-395
     TRY(ensure_vectors(ctx));
     StageTimer T(ctx, &ctx->tm.loads);
-    DevBuf<int64_t> d; CU(d.alloc(nnodes));
+    TmpBuf<int64_t> d(ctx->stream); CU(d.alloc(nnodes));
     CU(cudaMemcpyAsync(d.p, nodes, nnodes * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
     double inv = 1.0 / (double)nnodes;    // force_vector ./ length(nodes) (:401)
@@ -637,7 +637,7 @@ int add_volume_force(toe_ctx* ctx, const double b[3], double rho_uniform, const 
     }
     StageTimer T(ctx, &ctx->tm.loads);
     unsigned grid = div_up(ctx->nq, 128);
-    DevBuf<double> part; CU(part.alloc(grid + 1));
+    TmpBuf<double> part(ctx->stream); CU(part.alloc(grid + 1));
     // partitioned: the per-rank partial load goes to a scratch vector, is summed over the interface, then added to f
     double* target = ctx->f.p;
     size_t n = 3 * (size_t)ctx->nq;
@@ -796,7 +796,7 @@ int apply_dirichlet(toe_ctx* ctx, const int64_t* dofs, i64 nd, double* mean_out)
     size_t nglob = ctx->n_global ? (size_t)ctx->n_global : n;
     double inv_n = 1.0 / (double)nglob;
     if (nd > 0) {
-        DevBuf<int64_t> d; CU(d.alloc(nd));
+        TmpBuf<int64_t> d(ctx->stream); CU(d.alloc(nd));
         CU(cudaMemcpyAsync(d.p, dofs, nd * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(ctx->errflag.p + 2, 0, sizeof(int), ctx->stream));
         LAUNCH(ctx, k_mark_dirichlet, div_up(nd, 128), 128, 0, (const int64_t*)d.p, nd, nglob, ctx->glob2loc, (const double*)m_dev, inv_n,
@@ -864,7 +864,7 @@ __global__ void k_scalar_values(const int* __restrict__ blk_ptr, const double* _
 
 int get_node_dofs(toe_ctx* ctx, int64_t* out_host) {
     if (!ctx->have_dofs) return toe_fail(ctx, TOE_ERR_STATE, "DOFs not built");
-    DevBuf<int64_t> d; CU(d.alloc(ctx->nn));
+    TmpBuf<int64_t> d(ctx->stream); CU(d.alloc(ctx->nn));
     const int* nq_map = ctx->node_q.p;
     if (ctx->dist) TRY(dist_node_dofs(ctx, &nq_map));          // partitioned: ctx->node_q is the local map, the ABI wants the global one
     LAUNCH(ctx, k_node_first_dof, div_up(ctx->nn, 256), 256, 0, nq_map, d.p, ctx->nn);

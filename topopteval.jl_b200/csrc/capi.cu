@@ -81,6 +81,12 @@ int toe_create(int device, toe_ctx** out) {
     if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return TOE_ERR_CUDA; }
     toe_ctx* c = new toe_ctx();
     c->device = device;
+    {   // temporaries of the API calls come from the default memory pool (TmpBuf): keep what they free cached instead of returning it
+        cudaMemPool_t pool = nullptr;
+        unsigned long long keep = ~0ULL;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaGetLastError();
+    }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
         g_create_error = "failed to create stream/events";

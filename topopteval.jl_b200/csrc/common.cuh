@@ -43,6 +43,26 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// Temporary device buffer of ONE API call: stream-ordered allocation from the device's default memory pool (release threshold set to
+// "never" in toe_create), so that after the first call of a kind no allocation reaches the driver and — unlike cudaFree — freeing does
+// not synchronise the device.  Everything that touches the buffer must be enqueued on the same stream.
+template <typename T>
+struct TmpBuf {
+    T* p = nullptr;
+    cudaStream_t s;
+    explicit TmpBuf(cudaStream_t stream) : s(stream) {}
+    TmpBuf(const TmpBuf&) = delete;
+    TmpBuf& operator=(const TmpBuf&) = delete;
+    ~TmpBuf() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t alloc(size_t count) {
+        if (p) { cudaFreeAsync(p, s); p = nullptr; }
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), s);
+        if (e != cudaSuccess) p = nullptr;
+        return e;
+    }
+};
+
 enum MaterialMode { MAT_NONE = 0, MAT_UNIFORM = 1, MAT_SIMP = 2, MAT_PERCELL = 3 };
 
 // device-visible material description (passed by value to kernels)

@@ -68,7 +68,7 @@ int scan_exclusive_i32(toe_ctx* ctx, const int* in, int* out, i64 n, i64* total_
     if (n == 0) { CU(cudaMemsetAsync(out, 0, sizeof(int), ctx->stream)); if (total_out) *total_out = 0; return TOE_OK; }
     i64 ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     {   // overflow guard: the prefix sums are 32-bit, so the total must fit (checked in 64 bits BEFORE scanning; in may alias out)
-        DevBuf<unsigned long long> tot64; CU(tot64.alloc(1));
+        TmpBuf<unsigned long long> tot64(ctx->stream); CU(tot64.alloc(1));
         CU(cudaMemsetAsync(tot64.p, 0, sizeof(unsigned long long), ctx->stream));
         LAUNCH(ctx, k_total_i64, min_u(div_up(n, 256), 2048u), 256, 0, in, n, tot64.p);
         unsigned long long h = 0;
@@ -77,12 +77,12 @@ int scan_exclusive_i32(toe_ctx* ctx, const int* in, int* out, i64 n, i64* total_
         if (h > 2147483647ULL) return toe_fail(ctx, TOE_ERR_MESH, "index overflow: a prefix sum would reach %llu > 2^31-1", h);
     }
     // keep the last input element: aliasing would overwrite it before k_write_total reads it
-    DevBuf<int> last_in; CU(last_in.alloc(1));
+    TmpBuf<int> last_in(ctx->stream); CU(last_in.alloc(1));
     CU(cudaMemcpyAsync(last_in.p, in + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     if (ntiles == 1) {
         LAUNCH(ctx, k_scan_tiles, 1, SCAN_THREADS, 0, in, out, (const int*)nullptr, n);
     } else {
-        DevBuf<int> sums; CU(sums.alloc(ntiles + 1));
+        TmpBuf<int> sums(ctx->stream); CU(sums.alloc(ntiles + 1));
         LAUNCH(ctx, k_scan_tile_sums, (unsigned)ntiles, SCAN_THREADS, 0, in, sums.p, n);
         i64 dummy;
         TRY(scan_exclusive_i32(ctx, sums.p, sums.p, ntiles, &dummy));
@@ -129,7 +129,7 @@ int mesh_upload(toe_ctx* ctx, i64 nn, const double* xyz, i64 ne, int npc, const 
     CU(cudaMemsetAsync(ctx->errflag.p, 0, 4 * sizeof(int), ctx->stream));
     CU(cudaMemcpyAsync(ctx->xyz.p, xyz, 3 * nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     {
-        DevBuf<int64_t> tmp; CU(tmp.alloc(total));
+        TmpBuf<int64_t> tmp(ctx->stream); CU(tmp.alloc(total));
         CU(cudaMemcpyAsync(tmp.p, conn, total * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(ctx, k_conn_to_i32, div_up(total, 256), 256, 0, (const int64_t*)tmp.p, ctx->conn0.p, total, nn, ctx->errflag.p);
         int e = 0;
@@ -172,8 +172,8 @@ __global__ void k_cq(const int* __restrict__ conn0, const int* __restrict__ node
 int mesh_build_dofs(toe_ctx* ctx) {
     if (!ctx->have_mesh) return toe_fail(ctx, TOE_ERR_STATE, "toe_build_dofs: no mesh set");
     i64 total = ctx->ne * ctx->npc;
-    DevBuf<u64> key; CU(key.alloc(ctx->nn));
-    DevBuf<int> flag; CU(flag.alloc(total + 1));
+    TmpBuf<u64> key(ctx->stream); CU(key.alloc(ctx->nn));
+    TmpBuf<int> flag(ctx->stream); CU(flag.alloc(total + 1));
     LAUNCH(ctx, k_fill_u64, div_up(ctx->nn, 256), 256, 0, key.p, ~0ULL, ctx->nn);
     LAUNCH(ctx, k_first_touch, div_up(total, 256), 256, 0, (const int*)ctx->conn0.p, key.p, total);
     LAUNCH(ctx, k_flag_first, div_up(total, 256), 256, 0, (const int*)ctx->conn0.p, (const u64*)key.p, flag.p, total);
@@ -252,7 +252,7 @@ int mesh_build_pattern(toe_ctx* ctx) {
     CU(ctx->inc_ptr.alloc(nq + 1));
     CU(ctx->inc.alloc(total));
     {
-        DevBuf<int> cursor; CU(cursor.alloc(nq));
+        TmpBuf<int> cursor(ctx->stream); CU(cursor.alloc(nq));
         CU(cudaMemsetAsync(ctx->inc_ptr.p, 0, (nq + 1) * sizeof(int), ctx->stream));
         CU(cudaMemsetAsync(cursor.p, 0, nq * sizeof(int), ctx->stream));
         LAUNCH(ctx, k_count_inc, div_up(total, 256), 256, 0, (const int*)ctx->cq.p, ctx->inc_ptr.p, total);

@@ -874,8 +874,8 @@ int energy(toe_ctx* ctx, double* half_uKu, double* compliance, double* per_elem_
     int ne = (int)ctx->ne;
     StageTimer T(ctx, &ctx->tm.energy);
     unsigned grid = div_up(ne, 128);
-    DevBuf<double> part; CU(part.alloc(grid + 4));
-    DevBuf<double> ee;
+    TmpBuf<double> part(ctx->stream); CU(part.alloc(grid + 4));
+    TmpBuf<double> ee(ctx->stream);
     if (per_elem_host) CU(ee.alloc(ne));
     double* eep = per_elem_host ? ee.p : nullptr;
     if (ctx->npc == 4) LAUNCH(ctx, k_elem_energy<4>, grid, 128, 0, (const int*)ctx->cq.p, (const double*)ctx->xq.p, ctx->mat, (const double*)ctx->u.p, eep, ne, part.p);
