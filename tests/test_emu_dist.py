@@ -215,3 +215,44 @@ def test_partitioned_results_do_not_depend_on_block_order(emu):
                 assert np.array_equal(ref[rk][-1]["part"], got[rk][-1]["part"])
     finally:
         lib.emu_set_block_order(0)
+
+
+def test_cg_scalar_trace_is_consistent(emu, monkeypatch):
+    """toe_debug_cg_trace (TOE_CG_TRACE=1, the diagnostic that located the round-1 SpMV pipeline bug): per iteration the summed γ and δ are
+    identical on every rank and equal the rank-ordered sum of the ranks' partials, and √γ is the residual history."""
+    pkg, lib = emu
+    monkeypatch.setenv("TOE_CG_TRACE", "1")
+    prob = _problem(pkg, (10, 4, 2), False)
+    world = 2
+    uid = pkg.Context.comm_unique_id()
+    out, err = [None] * world, [None] * world
+
+    def worker(rank):
+        try:
+            ctx = pkg.Context(rank)
+            ctx.comm_init(world, rank, uid)
+            pts, cells, rho, fixed, load = prob
+            lam, mu = pkg.create_material_model(1.0, 0.3)
+            ctx.set_mesh(pts, cells, distributed=True); ctx.build_dofs(); ctx.build_pattern()
+            ctx.assemble_lame(lam, mu); ctx.add_nodal_force(load, [0.0, 0.0, -1.0])
+            nfd = ctx.node_dofs()
+            ctx.apply_dirichlet(np.sort((nfd[fixed - 1][:, None] + np.arange(3)[None, :]).reshape(-1)))
+            st = ctx.solve_pcg(1e-9, 1e-9, 5000, graph=False, history=True)
+            out[rank] = (st, ctx.cg_trace(st["niter"] + 1))
+            ctx.close()
+        except BaseException as ex:  # noqa: BLE001
+            err[rank] = ex
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(600)
+    assert err == [None, None], err
+    (st0, t0), (st1, t1) = out
+    n = st0["niter"]
+    assert st0["converged"] == 1 and st1["niter"] == n and t0.shape == (n + 1, 4)
+    assert np.array_equal(t0[:, :2], t1[:, :2])                                   # summed scalars: same bits on both ranks
+    assert np.array_equal(t0[1:, 0], t0[1:, 2] + t1[1:, 2])                       # γ_j = rank 0's partial + rank 1's, in rank order
+    assert np.array_equal(t0[1:, 1], t0[1:, 3] + t1[1:, 3])                       # δ_j likewise
+    assert np.array_equal(np.sqrt(t0[:, 0]), st0["residuals"])                   # √γ_j is the history Krylov.jl would report
