@@ -101,9 +101,9 @@ void toe_destroy(toe_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }   // before the communicator: a captured graph may hold NCCL work (TOE_DIST_GRAPH)
     dist_destroy(ctx);
     tl_destroy(ctx);
-    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     if (ctx->cgs_host) cudaFreeHost(ctx->cgs_host);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
