@@ -429,7 +429,7 @@ def run_b200(args, pkg, prog):
 
     h2d = pts.nbytes + cells.nbytes + load.nbytes + pres.nbytes
     d2h = u.nbytes + 2 * 8 + 128
-    info = {"ndofs": ctx.ndofs, "nnz": ctx.nnz, "transport": ctx.comm_info()["transport"]}
+    info = {"ndofs": ctx.ndofs, "nnz": ctx.nnz, "transport": ctx.comm_info()["transport"], "stale": ctx.stale_cuda_errors()}
     pcg_s = acc["solve"] / args.steps
     asm_rate = ne_total * args.steps / acc["assemble"] if acc["assemble"] > 0 else None
 
@@ -454,7 +454,7 @@ def run_b200(args, pkg, prog):
                        "pcg_seconds": pcg_s, "pcg_iterations_per_step": iters, "pcg_converged": True, "pcg_rel_res_l2": st["rel_res_l2"],
                        "spmv_gbs": spmv_bytes / spmv_s / 1e9, "energy_ms": 1e3 * acc["energy"] / args.steps,
                        "energy": e, "compliance": c, "local_sizes": sizes, "exchange": info["transport"], "ndofs": info["ndofs"], "nnz_local": info["nnz"],
-                       "wall_ms_per_step": 1e3 * wall_s / args.steps,
+                       "wall_ms_per_step": 1e3 * wall_s / args.steps, "stale_cuda_errors": {"count": info["stale"][0], "last": info["stale"][1]},
                        "setup_ms": {k: 1e3 * tm_setup[k] for k in ("set_mesh", "build_dofs", "build_pattern")},
                        "l2_criterion": l2, "two_level_preconditioner": two_level},
         }

@@ -81,6 +81,10 @@ int         toe_create(int device, toe_ctx** out);
 void        toe_destroy(toe_ctx* ctx);
 const char* toe_last_error(toe_ctx* ctx);            /* ctx may be NULL: error of the last failed toe_create */
 int         toe_get_timings(toe_ctx* ctx, toe_timings* out);
+/* CUDA errors that were pending in the runtime's last-error slot before one of this ctx's kernel launches (left behind by an earlier
+ * unchecked call); they never fail the launch they precede, but they are counted and the last one is kept (text owned by the ctx).
+ * TOE_VERBOSE=1 in the environment also prints them to stderr. */
+int         toe_debug_stale_cuda_errors(toe_ctx* ctx, int64_t* count_out, const char** last_out);
 /* device stopwatch on the ctx's own stream (CUDA events): what bench.py brackets its timed region with */
 int         toe_timer_start(toe_ctx* ctx);
 int         toe_timer_stop(toe_ctx* ctx, double* seconds_out);

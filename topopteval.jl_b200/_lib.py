@@ -50,6 +50,7 @@ SIGNATURES = {
     "toe_destroy": (None, [_P]),
     "toe_last_error": (C.c_char_p, [_P]),
     "toe_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
+    "toe_debug_stale_cuda_errors": (C.c_int, [_P, _I64, C.POINTER(C.c_char_p)]),
     "toe_timer_start": (C.c_int, [_P]),
     "toe_timer_stop": (C.c_int, [_P, _D]),
     "toe_set_mesh": (C.c_int, [_P, C.c_int64, _D, C.c_int64, C.c_int, _I64]),
@@ -433,6 +434,11 @@ class Context:
         s = C.c_double()
         self._ck(self.lib.toe_timer_stop(self.h, C.byref(s)))
         return s.value
+
+    def stale_cuda_errors(self):
+        n = C.c_int64(); msg = C.c_char_p()
+        self._ck(self.lib.toe_debug_stale_cuda_errors(self.h, C.byref(n), C.byref(msg)))
+        return n.value, (msg.value or b"").decode()
 
     def timings(self):
         t = Timings()

@@ -114,6 +114,13 @@ void toe_destroy(toe_ctx* ctx) {
     if (s) cudaStreamDestroy(s);
 }
 
+int toe_debug_stale_cuda_errors(toe_ctx* ctx, int64_t* count_out, const char** last_out) {
+    if (!ctx) return TOE_ERR_ARG;
+    if (count_out) *count_out = ctx->stale_cuda_errors;
+    if (last_out) *last_out = ctx->stale_err.c_str();
+    return TOE_OK;
+}
+
 int toe_get_timings(toe_ctx* ctx, toe_timings* out) {
     if (!ctx || !out) return TOE_ERR_ARG;
     *out = ctx->tm; out->kernel_launches = ctx->launches;

@@ -6,6 +6,7 @@
 #include <vector>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
 
 #include "../../include/topopt_b200.h"
 
@@ -103,6 +104,10 @@ struct toe_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
+    // CUDA errors found in the runtime's last-error slot BEFORE a launch: left behind by an earlier call nobody checked (an event record,
+    // a free, a library probing peer access …).  They are not this launch's, so they do not fail it — but they are not dropped either.
+    i64 stale_cuda_errors = 0;
+    std::string stale_err;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     toe_timings tm = {};
     i64 launches = 0;
@@ -199,12 +204,21 @@ inline int toe_fail(toe_ctx* c, int code, const char* fmt, ...) {
     return toe_fail(ctx, TOE_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e)); } } while (0)
 #define TRY(call) do { int _s = (call); if (_s != TOE_OK) return _s; } while (0)
 
+inline void toe_note_stale(toe_ctx* c, cudaError_t e, const char* before) {
+    c->stale_cuda_errors++;
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s (%s) was pending before the launch of %s", cudaGetErrorName(e), cudaGetErrorString(e), before);
+    c->stale_err = buf;
+    static const bool verbose = getenv("TOE_VERBOSE") != nullptr;
+    if (verbose) fprintf(stderr, "libtopopt_b200: stale CUDA error: %s\n", buf);
+}
+
 #ifndef TOE_EMU
 // a launch that the runtime refuses (bad configuration, shared-memory opt-in missing, sticky error) fails HERE, by kernel name, not
 // at some later synchronisation; cudaPeekAtLastError is a host-side read (also legal during stream capture)
-// (the slot is cleared first: a non-sticky error left behind by a library call — NCCL / IPC probing — has been handled by whoever made it)
+// (the slot is cleared first; what was in it is counted and kept: toe_debug_stale_cuda_errors)
 #define LAUNCH(ctx, kern, grid, block, smem, ...) do { \
-    (void)cudaGetLastError(); \
+    { cudaError_t _pe = cudaGetLastError(); if (_pe != cudaSuccess) toe_note_stale((ctx), _pe, #kern); } \
     kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; \
     cudaError_t _le = cudaPeekAtLastError(); \
     if (_le != cudaSuccess) return toe_fail((ctx), TOE_ERR_CUDA, "launch of %s <<<%u, %u, %zu B>>> failed: %s (%s)", #kern, (unsigned)(grid), (unsigned)(block), \
