@@ -371,6 +371,7 @@ class SolverConfig:
     drop_tolerance: float = 1e-4
     history: bool = False
     matrix_free: bool = False            # extension: element-by-element operator instead of the assembled K
+    l2_norm: bool = False                # extension: stop on ||r||_2 (TOE_PCG_L2_NORM) instead of Krylov.jl's M-norm rule (Jacobi only)
 
     def __post_init__(self):
         if self.max_iterations == 0:
@@ -466,7 +467,7 @@ def get_face_nodes(cell):
 DIRECT_EQUIVALENT_TOL = 1e-10
 
 
-def _solve(dh, constraints, tol, itmax, matrix_free, verbose, history=False, two_level=False, stress_material=None):
+def _solve(dh, constraints, tol, itmax, matrix_free, verbose, history=False, two_level=False, stress_material=None, l2_norm=False):
     """`stress_material`: keyword arguments of Context.calculate_stresses built from the CALLER's material arguments — the reference
     passes λ, μ (or material_model, density_data) of the solve call to calculate_stresses (FiniteElementAnalysis.jl:553 / :854), which
     may legally differ from what K was assembled with."""
@@ -475,7 +476,7 @@ def _solve(dh, constraints, tol, itmax, matrix_free, verbose, history=False, two
         ctx.apply_dirichlet(ch.prescribed_dofs)
     if verbose:
         print("Solving linear system...")
-    st = ctx.solve_pcg(tol, tol, itmax, matrix_free=matrix_free, history=history, two_level=two_level)
+    st = ctx.solve_pcg(tol, tol, itmax, matrix_free=matrix_free, history=history, two_level=two_level, l2_norm=l2_norm)
     if st["breakdown"]:
         raise TopOptError("CG breakdown: p'Ap <= 0 (matrix not positive definite)")
     if not st["converged"] and verbose:
@@ -518,7 +519,7 @@ def _robust(dh, constraints, config, stress_material):
         return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, _direct_itmax(dh), config.matrix_free, config.verbose, two_level=tl,
                       stress_material=stress_material)
     return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, config.history, two_level=tl,
-                  stress_material=stress_material)
+                  stress_material=stress_material, l2_norm=config.l2_norm)
 
 
 def solve_system_robust(K, f, dh, cellvalues, lam, mu, *constraints, config: SolverConfig | None = None):

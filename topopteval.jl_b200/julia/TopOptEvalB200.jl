@@ -224,6 +224,7 @@ Base.@kwdef struct SolverConfig
     drop_tolerance::Float64 = 1e-4
     history::Bool = false
     matrix_free::Bool = false        # extension: element-by-element operator
+    l2_norm::Bool = false            # extension: stop on ||r||_2 <= tol*(1 + ||r0||_2) (TOE_PCG_L2_NORM) instead of Krylov.jl's M-norm rule
 end
 
 struct PcgStats
@@ -295,7 +296,7 @@ const DIRECT_EQUIVALENT_TOL = 1e-10      # `K \ f` entry points run PCG to the a
 # `stress` = closure u -> (stress_field, max_von_mises, max_stress_cell) built from the CALLER's material arguments: the reference hands
 # λ, μ (or material_model, density_data) of the solve call to calculate_stresses (FiniteElementAnalysis.jl:553 / :854), and they may
 # legally differ from what K was assembled with
-function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbose, two_level, stress)
+function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbose, two_level, stress, l2_norm = false)
     c = dh.ctx
     for ch in constraints                                  # SINGLE APPLICATION POINT (:540-542)
         m = Ref(0.0)
@@ -304,7 +305,7 @@ function _solve(dh::B200DofHandler, constraints, tol, itmax, matrix_free, verbos
     verbose && println("Solving linear system...")
     st = Ref{PcgStats}()
     check(c, ccall((:toe_solve_pcg, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Int64, Cint, Ref{PcgStats}, Ptr{Float64}, Int64),
-                   c.ptr, tol, tol, itmax, (matrix_free ? 1 : 0) | (two_level ? 4 : 0), st, C_NULL, 0))      # TOE_PCG_MATRIX_FREE | TOE_PCG_TWO_LEVEL
+                   c.ptr, tol, tol, itmax, (matrix_free ? 1 : 0) | (two_level ? 4 : 0) | (l2_norm ? 8 : 0), st, C_NULL, 0))      # TOE_PCG_MATRIX_FREE | TOE_PCG_TWO_LEVEL | TOE_PCG_L2_NORM
     st[].breakdown != 0 && error("CG breakdown: p'Ap <= 0 (matrix not positive definite)")
     st[].converged == 0 && @warn "PCG did not converge in $(st[].niter) iterations (residual $(st[].res_M))"
     u = Vector{Float64}(undef, dh.ndofs)
@@ -332,7 +333,7 @@ function _robust(dh, constraints, config::SolverConfig, stress)
     # the GPU path, so PCG runs to the accuracy a direct solve delivers
     (config.method == :direct || (config.method == :auto && dh.ndofs < 50000)) &&
         return _solve(dh, constraints, DIRECT_EQUIVALENT_TOL, _direct_itmax(dh), config.matrix_free, config.verbose, tl, stress)
-    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, tl, stress)
+    return _solve(dh, constraints, config.tolerance, config.max_iterations, config.matrix_free, config.verbose, tl, stress, config.l2_norm)
 end
 solve_system_robust(K, f, dh, cv, λ, μ, constraints...; config::SolverConfig = SolverConfig()) =
     _robust(dh, constraints, config, u -> calculate_stresses(u, dh, cv, λ, μ))
