@@ -57,7 +57,7 @@ for _n in ["test_dofs_and_pattern_bit_exact", "test_dofs_permuted_cells_and_unre
            "test_ke_partial_range_and_errors", "test_assembled_K_tet", "test_assembled_K_hex_simp", "test_gather_assembly_is_deterministic_and_symmetric",
            "test_per_cell_lame_matches_simp", "test_loads", "test_volume_force_tet", "test_dirichlet_ferrite_semantics", "test_spmv_assembled_and_matrix_free",
            "test_stresses", "test_error_behaviour", "test_edge_single_cell_and_trivial_solves", "test_edge_duplicate_load_nodes_and_repeated_solves",
-           "test_edge_sliding_boundary_and_void_material", "test_edge_arbitrary_material_callable", "test_l2_norm_criterion_and_true_residual"]:
+           "test_edge_sliding_boundary_and_void_material", "test_edge_arbitrary_material_callable", "test_l2_norm_criterion_and_true_residual", "test_unstructured_delaunay_mesh"]:
     _adopt(_n)
 for _n in ["test_synthetic_cantilever_energies", "test_solve_c1_tet_beam", "test_pcg_krylov_semantics_and_iteration_count", "test_solve_c2_hex_simp", "test_runtests_recipe_linear_beam",
            "test_runtests_recipe_simp_beam", "test_gravity_cantilever_known_answer"]:

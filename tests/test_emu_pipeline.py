@@ -65,3 +65,17 @@ def test_pcg_with_out_of_order_fills_is_bit_identical(emu, monkeypatch):
         assert np.array_equal(st1["residuals"], st0["residuals"]) and np.array_equal(ctx.solution(), u0)
     finally:
         ctx.close()
+
+
+def test_partitioned_pcg_with_out_of_order_fills(emu, monkeypatch):
+    """the single-reduction CG of the partitioned path — the one that could not recover from a stale chunk — on 2 emulated ranks"""
+    import test_emu_dist as ed
+    pkg, lib = emu
+    prob = ed._problem(pkg, (16, 6, 3), False)
+    monkeypatch.setenv("TOE_SPMV_GRID", "2")
+    ref = ed._run_ranks(pkg, 2, prob, False, repeats=1, tol=1e-9)
+    monkeypatch.setenv("EMU_BULK_DELAY", "25")
+    got = ed._run_ranks(pkg, 2, prob, False, repeats=1, tol=1e-9)
+    for rk in range(2):
+        a, b = ref[rk][0], got[rk][0]
+        assert b["conv"] == 1 and b["brk"] == 0 and a["it"] == b["it"] and np.array_equal(a["u"], b["u"]), (rk, a["it"], b["it"])

@@ -668,3 +668,64 @@ def test_edge_arbitrary_material_callable(ctx, pkg, fo):
     assert np.max(np.abs(K.nzval() - prob.nzval)) <= 1e-12 * np.abs(prob.nzval).max()
     Ks = K.to_scipy()
     assert abs(Ks - prob.K()).max() <= 1e-12 * np.abs(prob.nzval).max()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# ragged input: unstructured Delaunay tets (irregular valence, arbitrary cell order, SIMP densities)
+# ----------------------------------------------------------------------------------------------------------
+def _delaunay_mesh(seed, npts):
+    """Random points in the 6x2x1 box → Delaunay tets, positively oriented, slivers dropped.  Node valences range from a handful to
+    several dozen cells, nothing like the 24 of the structured split."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    pts = rng.random((npts, 3)) * np.array([6.0, 2.0, 1.0])
+    corners = np.array([(x, y, z) for x in (0.0, 6.0) for y in (0.0, 2.0) for z in (0.0, 1.0)])
+    pts = np.vstack([corners, pts])
+    pts[8:8 + npts // 6, 0] = 0.0                                      # a populated clamp face ...
+    pts[8 + npts // 6:8 + npts // 3, 0] = 6.0                          # ... and a populated load face
+    tet = Delaunay(pts).simplices.astype(np.int64)
+    X = pts[tet]
+    vol = np.linalg.det(np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0], X[:, 3] - X[:, 0]], axis=2)) / 6.0
+    flip = vol < 0
+    tet[flip] = tet[flip][:, [0, 2, 1, 3]]
+    keep = np.abs(vol) > 1e-5
+    return pts, np.ascontiguousarray(tet[keep] + 1)
+
+
+@pytest.mark.parametrize("seed,npts", [(1, 120), (2, 260)])
+def test_unstructured_delaunay_mesh(ctx, pkg, fo, seed, npts):
+    pts, cells = _delaunay_mesh(seed, npts)
+    ne = cells.shape[0]
+    rho = np.random.default_rng(seed + 100).uniform(0.05, 1.0, ne)
+    _setup(ctx, pts, cells)
+    prob = fo.setup_problem(pts, cells)
+    assert np.array_equal(ctx.node_dofs(), prob.node_first_dof)
+    colptr, rowval = ctx.pattern()
+    assert np.array_equal(colptr, prob.colptr) and np.array_equal(rowval, prob.rowval)
+    fo.assemble_stiffness_matrix_simp(prob, fo.create_simp_material_model(1.0, 0.3, 1e-8, 3.0), rho)
+    scale = _row_scale(prob)
+    A = pkg._lib
+    vals = {}
+    for name, var in (("gather", A.ASM_GATHER), ("atomic", A.ASM_ATOMIC), ("rows", A.ASM_ROWS)):
+        ctx.assemble_simp(1.0, 0.3, 1e-8, 3.0, rho, var)
+        vals[name] = ctx.values()
+        assert np.max(np.abs(vals[name] - prob.nzval) / scale) <= TOL_KE, name
+    # loads, constraints, solve against the oracle's direct solve; assembled and matrix-free
+    fixed = pkg.meshgen.nodes_at_plane(pts, 0, 0.0); load = pkg.meshgen.nodes_at_plane(pts, 0, 6.0)
+    assert fixed.size >= 3 and load.size >= 3
+    fo.apply_force(prob, load, [0.0, 0.0, -1.0])
+    pres = fo.fixed_boundary_dofs(prob, fixed)
+    fo.apply_dirichlet(prob, pres)
+    uref = fo.solve_direct(prob)
+    eref = fo.deformation_energy(prob, uref)
+    x = np.random.default_rng(seed).standard_normal(ctx.ndofs)
+    for mf in (False, True):
+        (ctx.set_material_simp if mf else ctx.assemble_simp)(1.0, 0.3, 1e-8, 3.0, rho)
+        ctx.add_nodal_force(load, [0.0, 0.0, -1.0]); ctx.apply_dirichlet(pres)
+        y = ctx.spmv(x, matrix_free=mf)
+        assert np.max(np.abs(y - prob.K() @ x)) <= 1e-12 * np.max(np.abs(prob.K()).sum(axis=1)) * np.max(np.abs(x))
+        st = ctx.solve_pcg(1e-12, 1e-12, 200000, matrix_free=mf)
+        assert st["converged"] == 1 and st["breakdown"] == 0
+        assert rel(ctx.solution(), uref) <= TOL_U
+        e, c, ee = ctx.energy(per_element=True)
+        assert abs(e - eref) <= TOL_U * abs(eref) and abs(ee.sum() - e) <= 1e-11 * abs(e)
