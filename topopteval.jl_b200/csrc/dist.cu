@@ -172,13 +172,13 @@ int dist_allreduce(toe_ctx* ctx, double* dev_vals, int count) {
 }
 
 // Rendezvous of the ranks' streams: one 8-byte allreduce, then the host waits for it.  Set-up work differs per rank (host-side map
-// building, partition sizes), so the ranks reach the first exchange of a step up to ~100 ms apart; every broken-down partitioned solve
-// seen in round 1 was the FIRST solve after a set-up, the only place where such a skew exists.  Entering the exchange
-// sequences of a step in lock-step costs two ~20 µs collectives per step.
+// building, partition sizes), so the ranks reach the first exchange of a step up to ~100 ms apart; meeting here makes the ranks'
+// stage timers start together (two ~20 µs collectives per step).  Correctness does not depend on it (TOE_DIST_NO_ALIGN=1 runs clean;
+// the faults it was once added against were the SpMV pipeline's, profiles/r2_dist_diagnosis.md).
 int dist_align(toe_ctx* ctx) {
     DistState* d = ctx->dist;
     if (!d || d->nranks == 1) return TOE_OK;
-    static const bool off = getenv("TOE_DIST_NO_ALIGN") != nullptr;      // A/B switch for tools/dist_resetup_check.py
+    static const bool off = getenv("TOE_DIST_NO_ALIGN") != nullptr;      // A/B switch for tools/dist_diag.py
     if (off) return TOE_OK;
     TRY(ensure_vectors(ctx));
     double* slot = ctx->partials.p + PARTIALS_ALIGN_SLOT;
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_xchg(char* const* __restrict__
 // (re)creates the mailboxes and exchanges their IPC handles; collective.  Falls back to the NCCL path on any failure.
 static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host) {
     d->p2p_ok = false;
-    // opt-in (TOE_DIST_XCHG=p2p): one 4-GPU run at 10M tets timed out in the flag wait in round 1 (cause not found)
+    // opt-in (TOE_DIST_XCHG=p2p): 9 % faster than the all-gather at N=8, 1 % slower at N=4; clean in 38 solves at N=2/4/8
     if (d->nranks == 1 || xchg_mode() != XCHG_P2P) return TOE_OK;
     // agree on the receive-area stride
     int my_max = 1;

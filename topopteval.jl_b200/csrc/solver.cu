@@ -650,7 +650,7 @@ int solve_pcg(toe_ctx* ctx, double atol, double rtol, i64 itmax, int flags, toe_
         return (dist && !two_level) ? cgcg_iteration(ctx, matrix_free, n, hist_cap, k & 1, l2) : cg_iteration(ctx, matrix_free, n, hist_cap, two_level, l2);
     };
     bool use_graph = !(flags & TOE_PCG_NO_GRAPH);
-    if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture: opt-in (TOE_DIST_GRAPH=1) until measured
+    if (dist && !getenv("TOE_DIST_GRAPH")) use_graph = false;     // NCCL inside stream capture: opt-in (TOE_DIST_GRAPH=1) — 2-4 % faster, but processes did not exit cleanly in two runs
     i64 key = ((ctx->op_generation * 2 + l2) * 8 + (two_level ? 4 : 0) + matrix_free * 2 + 1) * 4096 + CG_BATCH;
     if (use_graph && (ctx->graph_key != key || !ctx->graph_exec)) {
         if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
