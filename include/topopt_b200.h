@@ -212,7 +212,8 @@ int toe_debug_cg_trace(toe_ctx* ctx, double* out, int64_t iterations);
 int toe_spmv_soak(toe_ctx* ctx, int matrix_free, int what, int64_t reps, int64_t* mismatching_batches, int64_t* mismatching_entries);
 
 /* ---- multi-GPU: one ctx per GPU / process, element-based domain decomposition --------------------------- */
-/* NCCL (dlopen'ed libnccl.so.2) send/recv for the interface-DOF exchange and allreduce for the CG scalars.
+/* NCCL (dlopen'ed libnccl.so.2) carries the interface-DOF exchange and the CG scalars (one all-gather per operator application by
+ * default; send/recv + allreduce or a peer-memory kernel on request — see toe_comm_info).
  * Rank 0 creates the id, the host (torch.distributed / MPI / Distributed.jl) broadcasts its 128 bytes. */
 int toe_comm_unique_id(char id_out[128]);
 int toe_comm_init(toe_ctx* ctx, int nranks, int rank, const char id[128]);
@@ -223,9 +224,9 @@ int toe_set_mesh_distributed(toe_ctx* ctx, int64_t nn, const double* xyz, int64_
 /* part id (0-based) of every global cell (ne int32) — identical on all ranks */
 int toe_get_partition(toe_ctx* ctx, int32_t* part_of_cell);
 int toe_local_sizes(toe_ctx* ctx, int64_t* ne_local, int64_t* ndofs_local, int64_t* nnz_local, int64_t* n_interface_dofs);
-/* transport of the per-iteration interface exchange: 0 = single GPU, 1 = NCCL send/recv + allreduce,
- * 2 = fused peer-memory kernel (CUDA IPC mailboxes over NVLink/NVSwitch; opt-in TOE_DIST_P2P=1, needs every rank to map every peer),
- * 3 = one ncclAllGather per exchange carrying interface values and scalars (opt-in TOE_DIST_XCHG=allgather) */
+/* transport of the per-iteration interface exchange: 0 = single GPU, 1 = NCCL send/recv + allreduce (TOE_DIST_XCHG=sendrecv),
+ * 2 = fused peer-memory kernel (CUDA IPC mailboxes over NVLink/NVSwitch; TOE_DIST_XCHG=p2p, needs every rank to map every peer),
+ * 3 = one ncclAllGather per exchange carrying interface values and CG scalars (the default) */
 int toe_comm_info(toe_ctx* ctx, int* nranks, int* rank, int* transport);
 
 #ifdef __cplusplus
