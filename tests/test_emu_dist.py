@@ -110,7 +110,7 @@ def test_partitioned_equals_single_ctx(emu, world, dims, simp, mf):
     r0 = ranks[0][-1]
     counts = np.bincount(r0["part"], minlength=world)
     assert counts.max() - counts.min() <= 1, counts
-    assert r0["transport"] == "nccl-allgather"                 # the default transport
+    assert r0["transport"] == ("peer-memory" if world >= 8 else "nccl-allgather")      # the default transport by world size
     for rk in range(world):
         first, r = ranks[rk][0], ranks[rk][-1]
         # every rank returns the same global answer, re-setups are bit-reproducible, and it equals the unpartitioned solve
@@ -139,6 +139,7 @@ def test_peer_memory_exchange_protocol(emu, world, dims, monkeypatch):
     pkg, lib = emu
     monkeypatch.setenv("EMU_JITTER", "1")
     prob = _problem(pkg, dims, False)
+    monkeypatch.setenv("TOE_DIST_XCHG", "allgather")
     nccl = _run_ranks(pkg, world, prob, False, repeats=1, tol=1e-9)
     monkeypatch.setenv("TOE_DIST_XCHG", "p2p")
     p2p = _run_ranks(pkg, world, prob, False, repeats=3, tol=1e-9)
@@ -159,7 +160,7 @@ def test_allgather_exchange_transport(emu, world, dims, simp, mf, monkeypatch):
     prob = _problem(pkg, dims, simp)
     monkeypatch.setenv("TOE_DIST_XCHG", "sendrecv")
     ref = _run_ranks(pkg, world, prob, mf, repeats=1, tol=1e-9)
-    monkeypatch.delenv("TOE_DIST_XCHG")
+    monkeypatch.setenv("TOE_DIST_XCHG", "allgather")
     ag = _run_ranks(pkg, world, prob, mf, repeats=2, tol=1e-9)
     assert ag[0][-1]["transport"] == "nccl-allgather" and ref[0][-1]["transport"] == "nccl"
     for rk in range(world):

@@ -104,18 +104,23 @@ static int exchange_allgather(toe_ctx* ctx, double* y, double* scal, int count);
 bool dist_active(toe_ctx* ctx) { return ctx->dist != nullptr; }
 
 // Transport of the per-iteration exchange (read at every set-up):
-//   allgather (default)  ONE ncclAllGather carries every rank's packed interface values and its partial scalars: one collective and
-//                        3 launches per exchange (3.11 s per 10M-tet solve at N=2 against 3.24 s for send/recv + allreduce)
-//   sendrecv             grouped ncclSend/ncclRecv per neighbour + ncclAllReduce of the scalars (TOE_DIST_XCHG=sendrecv)
-//   p2p                  fused peer-memory kernel over CUDA IPC mailboxes (TOE_DIST_XCHG=p2p or TOE_DIST_P2P=1)
-// All three do the same arithmetic in the same order (bit-identical iterates).  The transient CG faults of round 1 were NOT a transport
-// problem: they came from the SpMV's pipeline protocol (profiles/r2_dist_diagnosis.md); 48 of 48 solves are clean on either NCCL transport.
+//   allgather   ONE ncclAllGather carries every rank's packed interface values and its partial scalars: one collective and 3 launches
+//               per exchange.  Default below 8 ranks (10M tets: 3.11 s per solve at N=2 against 3.24 s for send/recv + allreduce and
+//               3.13 s for the peer-memory kernel; 1.836 s against 1.853 s for the peer-memory kernel at N=4).
+//   p2p         fused peer-memory kernel over CUDA IPC mailboxes: neighbour-only traffic, one launch.  Default from 8 ranks on, where
+//               the all-gather moves 8 slices to everybody (1 183 ms per 10M-tet step at N=8 against 1 304 ms for the all-gather and
+//               1 440 ms for send/recv + allreduce).  If the mailboxes cannot be set up (no peer access), the all-gather is used.
+//   sendrecv    grouped ncclSend/ncclRecv per neighbour + ncclAllReduce of the scalars — the literal north-star form.
+// TOE_DIST_XCHG=allgather|p2p|sendrecv forces one (TOE_DIST_P2P=1 = p2p).  All three do the same arithmetic in the same order
+// (bit-identical iterates).  The transient CG faults of round 1 were NOT a transport problem: they came from the SpMV's pipeline protocol
+// (profiles/r2_dist_diagnosis.md); 48 of 48 solves are clean on either NCCL transport, 38 of 38 on the peer-memory kernel.
 enum XchgMode { XCHG_ALLGATHER = 0, XCHG_SENDRECV = 1, XCHG_P2P = 2 };
-static XchgMode xchg_mode() {
+static XchgMode xchg_mode(int nranks) {
     const char* m = getenv("TOE_DIST_XCHG");
     if (m && strcmp(m, "sendrecv") == 0) return XCHG_SENDRECV;
+    if (m && strcmp(m, "allgather") == 0) return XCHG_ALLGATHER;
     if ((m && strcmp(m, "p2p") == 0) || (!m && getenv("TOE_DIST_P2P"))) return XCHG_P2P;
-    return XCHG_ALLGATHER;
+    return nranks >= 8 ? XCHG_P2P : XCHG_ALLGATHER;
 }
 
 static void mailbox_close_peers(DistState* d) {
@@ -606,7 +611,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) k_xchg(char* const* __restrict__
 static int mailbox_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host) {
     d->p2p_ok = false;
     // opt-in (TOE_DIST_XCHG=p2p): 9 % faster than the all-gather at N=8, 1 % slower at N=4; clean in 38 solves at N=2/4/8
-    if (d->nranks == 1 || xchg_mode() != XCHG_P2P) return TOE_OK;
+    if (d->nranks == 1 || xchg_mode(d->nranks) != XCHG_P2P) return TOE_OK;
     // agree on the receive-area stride
     int my_max = 1;
     for (int c : d->nbr_count) my_max = std::max(my_max, c);
@@ -722,7 +727,7 @@ __global__ void k_unpack_ag(const int* __restrict__ if_node, const int* __restri
 // collective; called at every set-up.  Publishes, for every (rank r, peer q), where r's segment for q starts in r's send layout.
 static int allgather_setup(toe_ctx* ctx, DistState* d, const std::vector<int>& if_src_host) {
     d->ag_ok = false;
-    if (d->nranks == 1 || xchg_mode() != XCHG_ALLGATHER || d->p2p_ok) return TOE_OK;
+    if (d->nranks == 1 || d->p2p_ok || xchg_mode(d->nranks) == XCHG_SENDRECV) return TOE_OK;      // all-gather: chosen, or the peer-memory set-up did not succeed
     const int R = d->nranks;
     std::vector<int> tab((size_t)R * R + 1, 0);                  // own row: 1 + offset of the segment for peer q (0 = not a neighbour); last: max n_shared_total
     for (size_t k = 0; k < d->nbr.size(); k++) tab[(size_t)d->rank * R + d->nbr[k]] = 1 + d->nbr_off[k];
