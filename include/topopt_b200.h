@@ -212,8 +212,9 @@ int toe_debug_cg_trace(toe_ctx* ctx, double* out, int64_t iterations);
 int toe_spmv_soak(toe_ctx* ctx, int matrix_free, int what, int64_t reps, int64_t* mismatching_batches, int64_t* mismatching_entries);
 
 /* ---- multi-GPU: one ctx per GPU / process, element-based domain decomposition --------------------------- */
-/* NCCL (dlopen'ed libnccl.so.2) carries the interface-DOF exchange and the CG scalars (one all-gather per operator application by
- * default; send/recv + allreduce or a peer-memory kernel on request — see toe_comm_info).
+/* The interface-DOF exchange and the CG scalars travel over NCCL (dlopen'ed libnccl.so.2; one all-gather per operator application,
+ * the default below 8 ranks; or send/recv + allreduce) or through a peer-memory kernel over NVLink (default from 8 ranks on) — see
+ * toe_comm_info and TOE_DIST_XCHG.
  * Rank 0 creates the id, the host (torch.distributed / MPI / Distributed.jl) broadcasts its 128 bytes. */
 int toe_comm_unique_id(char id_out[128]);
 int toe_comm_init(toe_ctx* ctx, int nranks, int rank, const char id[128]);
@@ -225,8 +226,9 @@ int toe_set_mesh_distributed(toe_ctx* ctx, int64_t nn, const double* xyz, int64_
 int toe_get_partition(toe_ctx* ctx, int32_t* part_of_cell);
 int toe_local_sizes(toe_ctx* ctx, int64_t* ne_local, int64_t* ndofs_local, int64_t* nnz_local, int64_t* n_interface_dofs);
 /* transport of the per-iteration interface exchange: 0 = single GPU, 1 = NCCL send/recv + allreduce (TOE_DIST_XCHG=sendrecv),
- * 2 = fused peer-memory kernel (CUDA IPC mailboxes over NVLink/NVSwitch; TOE_DIST_XCHG=p2p, needs every rank to map every peer),
- * 3 = one ncclAllGather per exchange carrying interface values and CG scalars (the default) */
+ * 2 = fused peer-memory kernel (CUDA IPC mailboxes over NVLink/NVSwitch; default from 8 ranks on, TOE_DIST_XCHG=p2p; needs every
+ *     rank to map every peer, else 3 is used),
+ * 3 = one ncclAllGather per exchange carrying interface values and CG scalars (default below 8 ranks, TOE_DIST_XCHG=allgather) */
 int toe_comm_info(toe_ctx* ctx, int* nranks, int* rank, int* transport);
 
 #ifdef __cplusplus
